@@ -1,0 +1,195 @@
+"""ctypes bindings of libseismic_b200.so (the C ABI declared in include/seismic_b200.h) + in-tree build.
+
+The library is compiled in-tree (seismic_b200/_lib/) by `build_native()` with
+`nvcc -gencode arch=compute_100a,code=sm_100a`; there is no CPU fallback for the search path: if the
+library is missing the import fails loudly, and the sgpu_* calls fail with SGPU_ECUDA without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+REPO = ROOT.parent
+LIB_DIR = ROOT / "_lib"
+LIB_PATH = LIB_DIR / "libseismic_b200.so"
+HOST_SRC = sorted((ROOT / "csrc" / "host").glob("*.cpp"))
+CUDA_SRC = [ROOT / "csrc" / "cuda" / "sgpu_api.cu"]
+HEADERS = (
+    sorted((ROOT / "csrc" / "host").glob("*.hpp"))
+    + sorted((ROOT / "csrc" / "cuda").glob("*.cuh"))
+    + [REPO / "include" / "seismic_b200.h"]
+)
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-pthread,-O3,-march=x86-64-v3", "-shared",
+]
+
+
+def _stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in HOST_SRC + CUDA_SRC + HEADERS)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA + host sources into seismic_b200/_lib/libseismic_b200.so for sm_100a."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    LIB_DIR.mkdir(exist_ok=True)
+    tmp = LIB_DIR / (".build_%d.so" % os.getpid())
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp), *map(str, CUDA_SRC), *map(str, HOST_SRC)]
+    if verbose:
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+# ---------------------------------------------------------------------------------- structs
+class IndexView(C.Structure):
+    _fields_ = [
+        ("comp_bits", C.c_uint32), ("value_kind", C.c_uint32), ("n_docs", C.c_uint64), ("dim", C.c_uint64),
+        ("value_scale", C.c_float), ("reserved0", C.c_uint32),
+        ("fwd_offsets", C.c_void_p), ("fwd_comps", C.c_void_p), ("fwd_values", C.c_void_p), ("fwd_nnz", C.c_void_p),
+        ("list_post_start", C.c_void_p), ("postings", C.c_void_p), ("list_blk_start", C.c_void_p),
+        ("blk_post_off", C.c_void_p), ("blk_min", C.c_void_p), ("blk_quant", C.c_void_p),
+        ("list_sc_start", C.c_void_p), ("sc_comp", C.c_void_p), ("list_ent_start", C.c_void_p),
+        ("sc_run_off", C.c_void_p), ("ent_blk", C.c_void_p), ("ent_code", C.c_void_p),
+    ]
+
+
+class QueryBatch(C.Structure):
+    _fields_ = [("n_queries", C.c_uint64), ("offsets", C.c_void_p), ("comps", C.c_void_p), ("values", C.c_void_p)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("query_cut", C.c_uint32), ("heap_factor", C.c_float), ("n_knn", C.c_uint32),
+                ("first_sorted", C.c_int32)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_prep", C.c_float), ("ms_summary", C.c_float), ("ms_search", C.c_float),
+                ("ms_finish", C.c_float), ("n_launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("docs_scored", C.c_uint64), ("blocks_scored", C.c_uint64), ("blocks_pushed", C.c_uint64),
+                ("fwd_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class BuildConfig(C.Structure):
+    _fields_ = [("pruning", C.c_uint32), ("n_postings", C.c_uint32), ("max_fraction", C.c_float),
+                ("blocking", C.c_uint32), ("centroid_fraction", C.c_float), ("min_cluster_size", C.c_uint32),
+                ("doc_cut", C.c_uint32), ("block_size", C.c_uint32), ("summarization", C.c_uint32),
+                ("summary_energy", C.c_float), ("n_components", C.c_uint32), ("comp_bits", C.c_uint32),
+                ("value_kind", C.c_uint32), ("n_threads", C.c_uint32), ("kmeans_seed", C.c_uint64)]
+
+
+class SynthConfig(C.Structure):
+    _fields_ = [("n_docs", C.c_uint64), ("dim", C.c_uint64), ("seed", C.c_uint64), ("n_topics", C.c_uint32),
+                ("topic_terms", C.c_uint32), ("doc_nnz_mean", C.c_float), ("doc_nnz_sigma", C.c_float),
+                ("query_nnz_mean", C.c_float), ("query_nnz_sigma", C.c_float), ("n_threads", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+VAL_F16, VAL_BF16, VAL_F32, VAL_FIXEDU8, VAL_FIXEDU16, VAL_DOTVBYTE = range(6)
+PAD_ID = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+# every symbol include/seismic_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = {
+    "sgpu_index_create": (C.c_int, [C.POINTER(IndexView), C.c_int, C.POINTER(C.c_void_p)]),
+    "sgpu_index_destroy": (None, [C.c_void_p]),
+    "sgpu_index_device_bytes": (C.c_uint64, [C.c_void_p]),
+    "sgpu_batch_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.POINTER(SearchParams), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.POINTER(SearchStats)]),
+    "sgpu_batch_search_device": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.POINTER(SearchParams), C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.POINTER(SearchStats)]),
+    "sgpu_index_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "sgpu_exact_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.c_uint32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(C.c_float)]),
+    "sgpu_last_error": (C.c_char_p, []),
+    "sgpu_version": (C.c_char_p, []),
+    "shost_default_config": (None, [C.POINTER(BuildConfig)]),
+    "shost_default_synth": (None, [C.POINTER(SynthConfig)]),
+    "shost_dataset_create": (C.c_int, [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_void_p)]),
+    "shost_dataset_read_bin": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "shost_dataset_write_bin": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "shost_dataset_destroy": (None, [C.c_void_p]),
+    "shost_dataset_len": (C.c_uint64, [C.c_void_p]),
+    "shost_dataset_dim": (C.c_uint64, [C.c_void_p]),
+    "shost_dataset_nnz": (C.c_uint64, [C.c_void_p]),
+    "shost_dataset_offsets": (C.c_void_p, [C.c_void_p]),
+    "shost_dataset_comps": (C.c_void_p, [C.c_void_p]),
+    "shost_dataset_values": (C.c_void_p, [C.c_void_p]),
+    "shost_synth_documents": (C.c_int, [C.POINTER(SynthConfig), C.POINTER(C.c_void_p)]),
+    "shost_synth_queries": (C.c_int, [C.POINTER(SynthConfig), C.c_uint64, C.POINTER(C.c_void_p)]),
+    "shost_index_build": (C.c_int, [C.c_void_p, C.POINTER(BuildConfig), C.POINTER(C.c_void_p)]),
+    "shost_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "shost_index_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "shost_index_destroy": (None, [C.c_void_p]),
+    "shost_index_view": (C.c_int, [C.c_void_p, C.POINTER(IndexView)]),
+    "shost_index_nnz": (C.c_uint64, [C.c_void_p]),
+    "shost_index_space_usage": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "shost_index_get_doc": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
+                                      C.POINTER(C.c_uint32)]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the sources are newer) the native library. Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            build_native()
+        elif not LIB_PATH.exists():
+            raise ImportError(
+                "seismic_b200: native library %s is missing and nvcc is not available; "
+                "run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+    handle = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return handle
+
+
+class SeismicError(RuntimeError):
+    pass
+
+
+_ERR = {-1: ValueError, -2: SeismicError, -3: MemoryError, -4: OSError, -5: NotImplementedError}
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().sgpu_last_error().decode("utf-8", "replace")
+        raise _ERR.get(rc, SeismicError)(msg or ("seismic_b200 error %d" % rc))
+
+
+def ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def np_view(address: int, count: int, dtype) -> np.ndarray:
+    """Borrowed numpy view of `count` items at a native address (the owner must stay alive)."""
+    dt = np.dtype(dtype)
+    if count == 0 or not address:
+        return np.empty(0, dtype=dt)
+    buf = (C.c_uint8 * (count * dt.itemsize)).from_address(address)
+    return np.frombuffer(buf, dtype=dt, count=count)

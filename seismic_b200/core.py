@@ -1,0 +1,291 @@
+"""Low-level Python objects over the C ABI: Dataset, HostIndex (CPU build / persistence) and GpuIndex
+(the HBM image + batched search).  The `seismic`-compatible classes live in seismic_b200/api.py."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def csr_from_lists(components: Sequence[np.ndarray], values: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Concatenate per-vector arrays into (offsets u64, comps u32, values f32)."""
+    n = len(components)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    if n:
+        offsets[1:] = np.cumsum([len(c) for c in components], dtype=np.uint64)
+    comps = np.concatenate([np.asarray(c, dtype=np.uint32) for c in components]) if n and offsets[-1] else np.empty(0, np.uint32)
+    vals = np.concatenate([np.asarray(v, dtype=np.float32) for v in values]) if n and offsets[-1] else np.empty(0, np.float32)
+    return offsets, np.ascontiguousarray(comps, dtype=np.uint32), np.ascontiguousarray(vals, dtype=np.float32)
+
+
+class Dataset:
+    """Sparse dataset (CSR, u32 components, f32 values) owned by the native library."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().shost_dataset_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    @staticmethod
+    def from_csr(offsets, comps, values, dim: int) -> "Dataset":
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        comps = np.ascontiguousarray(comps, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        if len(comps) != len(values) or int(offsets[-1]) != len(comps):
+            raise ValueError("inconsistent CSR arrays")
+        out = C.c_void_p()
+        N.check(N.lib().shost_dataset_create(len(offsets) - 1, dim, N.ptr(offsets), N.ptr(comps), N.ptr(values), C.byref(out)))
+        return Dataset(out.value)
+
+    @staticmethod
+    def from_lists(components, values, dim: Optional[int] = None) -> "Dataset":
+        off, c, v = csr_from_lists(components, values)
+        if dim is None:
+            dim = int(c.max()) + 1 if len(c) else 0
+        return Dataset.from_csr(off, c, v, dim)
+
+    @staticmethod
+    def read_bin(path: str) -> "Dataset":
+        out = C.c_void_p()
+        N.check(N.lib().shost_dataset_read_bin(str(path).encode(), C.byref(out)))
+        return Dataset(out.value)
+
+    def write_bin(self, path: str) -> None:
+        N.check(N.lib().shost_dataset_write_bin(self._h, str(path).encode()))
+
+    @staticmethod
+    def synth_config(n_docs: int, dim: int = 30522, seed: int = 20260517, n_topics: Optional[int] = None, **kw) -> N.SynthConfig:
+        cfg = N.SynthConfig()
+        N.lib().shost_default_synth(C.byref(cfg))
+        cfg.n_docs, cfg.dim, cfg.seed = n_docs, dim, seed
+        # keep ~2150 documents per topic at every scale (4096 topics at 8.8 M documents)
+        cfg.n_topics = n_topics if n_topics else int(min(4096, max(16, n_docs // 2150)))
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    @staticmethod
+    def synth_documents(cfg: N.SynthConfig) -> "Dataset":
+        out = C.c_void_p()
+        N.check(N.lib().shost_synth_documents(C.byref(cfg), C.byref(out)))
+        return Dataset(out.value)
+
+    @staticmethod
+    def synth_queries(cfg: N.SynthConfig, n_queries: int) -> "Dataset":
+        out = C.c_void_p()
+        N.check(N.lib().shost_synth_queries(C.byref(cfg), n_queries, C.byref(out)))
+        return Dataset(out.value)
+
+    def __len__(self) -> int:
+        return int(N.lib().shost_dataset_len(self._h))
+
+    @property
+    def dim(self) -> int:
+        return int(N.lib().shost_dataset_dim(self._h))
+
+    @property
+    def nnz(self) -> int:
+        return int(N.lib().shost_dataset_nnz(self._h))
+
+    # borrowed views (valid while `self` is alive)
+    @property
+    def offsets(self) -> np.ndarray:
+        return N.np_view(N.lib().shost_dataset_offsets(self._h), len(self) + 1, np.uint64)
+
+    @property
+    def comps(self) -> np.ndarray:
+        return N.np_view(N.lib().shost_dataset_comps(self._h), self.nnz, np.uint32)
+
+    @property
+    def values(self) -> np.ndarray:
+        return N.np_view(N.lib().shost_dataset_values(self._h), self.nnz, np.float32)
+
+    def vector(self, i: int) -> Tuple[np.ndarray, np.ndarray]:
+        o = self.offsets
+        return self.comps[int(o[i]):int(o[i + 1])], self.values[int(o[i]):int(o[i + 1])]
+
+
+def make_config(n_postings=3500, centroid_fraction=0.1, min_cluster_size=2, summary_energy=0.4, max_fraction=1.5,
+                doc_cut=15, comp_bits=16, value_kind=N.VAL_F16, n_threads=0, **extra) -> N.BuildConfig:
+    """ShostBuildConfig with the Python defaults of the reference (src/pylib/mod.rs:329)."""
+    cfg = N.BuildConfig()
+    N.lib().shost_default_config(C.byref(cfg))
+    cfg.n_postings, cfg.centroid_fraction, cfg.min_cluster_size = n_postings, centroid_fraction, min_cluster_size
+    cfg.summary_energy, cfg.max_fraction, cfg.doc_cut = summary_energy, max_fraction, doc_cut
+    cfg.comp_bits, cfg.value_kind, cfg.n_threads = comp_bits, value_kind, n_threads
+    for k, v in extra.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+class HostIndex:
+    """Logical Seismic index in host memory (built on the CPU or mmap-loaded)."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        self._view = N.IndexView()
+        N.check(N.lib().shost_index_view(self._h, C.byref(self._view)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().shost_index_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    @staticmethod
+    def build(dataset: Dataset, config: Optional[N.BuildConfig] = None, **params) -> "HostIndex":
+        cfg = config if config is not None else make_config(**params)
+        out = C.c_void_p()
+        N.check(N.lib().shost_index_build(dataset._h, C.byref(cfg), C.byref(out)))
+        return HostIndex(out.value)
+
+    @staticmethod
+    def load(path: str) -> "HostIndex":
+        out = C.c_void_p()
+        N.check(N.lib().shost_index_load(str(path).encode(), C.byref(out)))
+        return HostIndex(out.value)
+
+    def save(self, path: str) -> None:
+        N.check(N.lib().shost_index_save(self._h, str(path).encode()))
+
+    @property
+    def view(self) -> N.IndexView:
+        return self._view
+
+    @property
+    def len(self) -> int:
+        return int(self._view.n_docs)
+
+    @property
+    def dim(self) -> int:
+        return int(self._view.dim)
+
+    @property
+    def nnz(self) -> int:
+        return int(N.lib().shost_index_nnz(self._h))
+
+    @property
+    def comp_bits(self) -> int:
+        return int(self._view.comp_bits)
+
+    def space_usage(self) -> dict:
+        b = (C.c_uint64 * 6)()
+        N.check(N.lib().shost_index_space_usage(self._h, b))
+        return dict(zip(["forward", "packed_postings", "block_offsets", "summaries", "knn", "total"], map(int, b)))
+
+    def get_doc(self, i: int) -> Tuple[np.ndarray, np.ndarray]:
+        cap = 65536
+        comps = np.empty(cap, np.uint32)
+        vals = np.empty(cap, np.float32)
+        n = C.c_uint32()
+        N.check(N.lib().shost_index_get_doc(self._h, i, N.ptr(comps), N.ptr(vals), cap, C.byref(n)))
+        return comps[: n.value].copy(), vals[: n.value].copy()
+
+    # numpy views of the logical arrays (tests, tools)
+    def arrays(self) -> dict:
+        v = self._view
+        dim, n = int(v.dim), int(v.n_docs)
+        lps = N.np_view(v.list_post_start, dim + 1, np.uint64)
+        lbs = N.np_view(v.list_blk_start, dim + 1, np.uint64)
+        lss = N.np_view(v.list_sc_start, dim + 1, np.uint64)
+        les = N.np_view(v.list_ent_start, dim + 1, np.uint64)
+        fo = N.np_view(v.fwd_offsets, n + 1, np.uint64)
+        return {
+            "fwd_offsets": fo,
+            "fwd_comps": N.np_view(v.fwd_comps, int(fo[-1]), np.uint16 if v.comp_bits == 16 else np.uint32),
+            "list_post_start": lps, "postings": N.np_view(v.postings, int(lps[-1]), np.uint64),
+            "list_blk_start": lbs, "blk_post_off": N.np_view(v.blk_post_off, int(lbs[-1]) + dim, np.uint32),
+            "blk_min": N.np_view(v.blk_min, int(lbs[-1]), np.float32),
+            "blk_quant": N.np_view(v.blk_quant, int(lbs[-1]), np.float32),
+            "list_sc_start": lss, "sc_comp": N.np_view(v.sc_comp, int(lss[-1]), np.uint32),
+            "list_ent_start": les, "sc_run_off": N.np_view(v.sc_run_off, int(lss[-1]) + dim, np.uint32),
+            "ent_blk": N.np_view(v.ent_blk, int(les[-1]), np.uint16),
+            "ent_code": N.np_view(v.ent_code, int(les[-1]), np.uint8),
+        }
+
+
+class GpuIndex:
+    """HBM image of a HostIndex on one CUDA device + the batched search entry points."""
+
+    def __init__(self, host: HostIndex, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().sgpu_index_create(C.byref(host.view), device, C.byref(self._h)))
+        self.device = device
+        self.dim = host.dim
+        self.len = host.len
+        self.last_stats: dict = {}
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().sgpu_index_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    @property
+    def device_bytes(self) -> int:
+        return int(N.lib().sgpu_index_device_bytes(self._h))
+
+    def set_option(self, name: str, value: int) -> None:
+        N.check(N.lib().sgpu_index_set_option(self._h, name.encode(), int(value)))
+
+    @staticmethod
+    def _params(k, query_cut, heap_factor, n_knn, first_sorted) -> N.SearchParams:
+        if k <= 0:
+            raise ValueError("k must be > 0")
+        return N.SearchParams(int(k), int(query_cut), float(heap_factor), int(n_knn), 1 if first_sorted else 0)
+
+    def batch_search(self, offsets, comps, values, k, query_cut, heap_factor, n_knn=0, first_sorted=True):
+        """Host buffers in, host buffers out (H2D/D2H inside the call). Returns ids[nq,k], scores[nq,k], counts[nq]."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        comps = np.ascontiguousarray(comps, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        nq = len(offsets) - 1
+        ids = np.empty((nq, k), dtype=np.uint64)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.uint32)
+        qb = N.QueryBatch(nq, N.ptr(offsets), N.ptr(comps), N.ptr(values))
+        p = self._params(k, query_cut, heap_factor, n_knn, first_sorted)
+        st = N.SearchStats()
+        N.check(N.lib().sgpu_batch_search(self._h, C.byref(qb), C.byref(p), N.ptr(ids), N.ptr(scores), N.ptr(counts), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return ids, scores, counts
+
+    def batch_search_device(self, d_offsets, d_comps, d_values, nq, k, query_cut, heap_factor, d_ids, d_scores,
+                            d_counts, n_knn=0, first_sorted=True) -> dict:
+        """All arguments are raw device pointers (ints, e.g. torch.Tensor.data_ptr()) on this index's device."""
+        qb = N.QueryBatch(nq, d_offsets, d_comps, d_values)
+        p = self._params(k, query_cut, heap_factor, n_knn, first_sorted)
+        st = N.SearchStats()
+        N.check(N.lib().sgpu_batch_search_device(self._h, C.byref(qb), C.byref(p), d_ids, d_scores, d_counts, C.byref(st)))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def exact_search(self, offsets, comps, values, k):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        comps = np.ascontiguousarray(comps, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        nq = len(offsets) - 1
+        ids = np.empty((nq, k), dtype=np.uint64)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.uint32)
+        qb = N.QueryBatch(nq, N.ptr(offsets), N.ptr(comps), N.ptr(values))
+        ms = C.c_float()
+        N.check(N.lib().sgpu_exact_search(self._h, C.byref(qb), int(k), N.ptr(ids), N.ptr(scores), N.ptr(counts), C.byref(ms)))
+        self.last_stats = {"ms_exact": ms.value}
+        return ids, scores, counts
+
+
+def recall_at_k(exact_ids: np.ndarray, exact_counts: np.ndarray, run_ids: np.ndarray, run_counts: np.ndarray) -> float:
+    """accuracy@k = sum_q |gt_q ∩ run_q| / sum_q |gt_q| (reference scripts/run_experiments.py:287-309)."""
+    hit = 0
+    tot = 0
+    for q in range(len(exact_counts)):
+        gt = set(exact_ids[q, : int(exact_counts[q])].tolist())
+        rn = set(run_ids[q, : int(run_counts[q])].tolist())
+        hit += len(gt & rn)
+        tot += len(gt)
+    return hit / tot if tot else 1.0

@@ -1,0 +1,583 @@
+// sgpu_* C ABI: HBM image construction and the batched search driver (see include/seismic_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/seismic_b200.h"
+#include "exact.cuh"
+#include "kernels.cuh"
+
+namespace shost {
+void set_error(const std::string& msg);
+}
+
+namespace {
+
+using namespace sgpu;
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            shost::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+            return _e == cudaErrorMemoryAllocation ? SGPU_ENOMEM : SGPU_ECUDA;                           \
+        }                                                                                                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t ensure(size_t n) {  // grow-only
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n ? n : 1);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, n ? n : 1);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct SgpuIndex {
+    int device = 0;
+    int n_sm = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // image
+    DevBuf lists, postings, blk_post_off, blk_min, blk_quant, sc_comp, sc_run_off, ent_blk, ent_code, fwd, rec_start;
+    sgpu::DevIndex ix{};
+    uint64_t image_bytes = 0;
+    uint32_t max_blocks = 0;      // largest number of blocks of any list
+    uint32_t max_block_docs = 0;  // largest block
+    // options
+    uint32_t wave_docs = 2048, first_wave_docs = 256;
+    int ctas = 0;
+    uint64_t scratch_bytes = 1ull << 30;
+    // per-batch scratch (grow-only)
+    DevBuf d_qoff, d_qcomps, d_qvals, d_nterms, d_status, d_counters, d_terms, d_est, d_order, d_keys, d_stats;
+    DevBuf d_out_ids, d_out_scores, d_out_counts, d_gdocs, d_gscores;
+    PinnedBuf h_in, h_out;
+    ~SgpuIndex() {
+        cudaSetDevice(device);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+template <class T>
+int upload(DevBuf& dst, const T* src, size_t n, cudaStream_t st, uint64_t* total) {
+    CK(dst.ensure(n * sizeof(T)));
+    if (n) CK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    *total += n * sizeof(T);
+    return SGPU_OK;
+}
+
+int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
+    if (!v || !out) {
+        shost::set_error("sgpu_index_create: null argument");
+        return SGPU_EINVAL;
+    }
+    if (v->comp_bits != 16 || v->value_kind != SGPU_VAL_F16) {
+        shost::set_error("sgpu_index_create: this build supports u16 components with f16 values");
+        return SGPU_EUNSUPPORTED;
+    }
+    if (v->dim > 65536 || v->dim == 0) {
+        shost::set_error("sgpu_index_create: dim must be in [1, 65536] for u16 components");
+        return SGPU_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        shost::set_error("no CUDA device available (seismic_b200 has no CPU fallback)");
+        return SGPU_ECUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        shost::set_error("sgpu_index_create: bad device ordinal");
+        return SGPU_EINVAL;
+    }
+    CK(cudaSetDevice(device));
+    std::unique_ptr<SgpuIndex> ix(new SgpuIndex());
+    ix->device = device;
+    CK(cudaDeviceGetAttribute(&ix->n_sm, cudaDevAttrMultiProcessorCount, device));
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    ix->smem_optin = (size_t)optin;
+    ix->ctas = ix->n_sm;
+    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& e : ix->ev) CK(cudaEventCreate(&e));
+    cudaStream_t st = ix->stream;
+    const uint64_t N = v->n_docs, dim = v->dim;
+    uint64_t total = 0;
+
+    // ---- record layout
+    std::vector<uint32_t> rec_start(N + 1);
+    {
+        uint64_t units = 0;
+        for (uint64_t d = 0; d < N; ++d) {
+            rec_start[d] = (uint32_t)units;
+            uint64_t len = v->fwd_offsets[d + 1] - v->fwd_offsets[d];
+            if (len > 65535) {
+                shost::set_error("document longer than 65535 components");
+                return SGPU_EINVAL;
+            }
+            units += (len + 7) >> 3;
+            if (units >= (1ull << 32)) {
+                shost::set_error("forward index larger than 2^32 32-byte units");
+                return SGPU_EUNSUPPORTED;
+            }
+        }
+        rec_start[N] = (uint32_t)units;
+        CK(ix->fwd.ensure(std::max<uint64_t>(units, 1) * 32));
+        total += units * 32;
+    }
+    if (int rc = upload(ix->rec_start, rec_start.data(), N + 1, st, &total)) return rc;
+    DevBuf d_fwd_off;
+    uint64_t scratch_total = 0;
+    if (int rc = upload(d_fwd_off, v->fwd_offsets, N + 1, st, &scratch_total)) return rc;
+    {
+        // pack records on the GPU, ~64 M elements per slice
+        const uint64_t slice_elems = 64ull << 20;
+        DevBuf d_c, d_v;
+        uint64_t d0 = 0;
+        while (d0 < N) {
+            uint64_t d1 = d0, e0 = v->fwd_offsets[d0];
+            while (d1 < N && v->fwd_offsets[d1 + 1] - e0 <= slice_elems) ++d1;
+            if (d1 == d0) d1 = d0 + 1;
+            const uint64_t ne = v->fwd_offsets[d1] - e0;
+            CK(d_c.ensure(std::max<uint64_t>(ne, 1) * 2));
+            CK(d_v.ensure(std::max<uint64_t>(ne, 1) * 2));
+            if (ne) {
+                CK(cudaMemcpyAsync(d_c.p, (const uint16_t*)v->fwd_comps + e0, ne * 2, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(d_v.p, (const uint16_t*)v->fwd_values + e0, ne * 2, cudaMemcpyHostToDevice, st));
+            }
+            const uint64_t nd = d1 - d0;
+            const unsigned blocks = (unsigned)((nd + 7) / 8);
+            k_pack_records<<<blocks, 256, 0, st>>>(d_fwd_off.as<uint64_t>(), d_c.as<uint16_t>(), d_v.as<uint16_t>(),
+                                                   ix->rec_start.as<uint32_t>(), d0, nd, e0, ix->fwd.as<uint16_t>());
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            d0 = d1;
+        }
+    }
+    // ---- posting lists
+    const uint64_t P = v->list_post_start[dim], TB = v->list_blk_start[dim], TSC = v->list_sc_start[dim],
+                   TE = v->list_ent_start[dim];
+    std::vector<ListHdr> hdr(dim);
+    uint32_t max_blocks = 0, max_block_docs = 0;
+    for (uint64_t l = 0; l < dim; ++l) {
+        ListHdr& h = hdr[l];
+        h.post_base = v->list_post_start[l];
+        h.ent_base = v->list_ent_start[l];
+        h.sc_base = v->list_sc_start[l];
+        h.blk_base = v->list_blk_start[l];
+        h.n_blk = (uint32_t)(v->list_blk_start[l + 1] - v->list_blk_start[l]);
+        h.n_sc = (uint32_t)(v->list_sc_start[l + 1] - v->list_sc_start[l]);
+        h.n_post = (uint32_t)(v->list_post_start[l + 1] - v->list_post_start[l]);
+        h.pad = 0;
+        if (h.n_blk > 65535) {
+            shost::set_error("list with more than 65535 blocks");
+            return SGPU_EINVAL;
+        }
+        max_blocks = std::max(max_blocks, h.n_blk);
+        const uint32_t* bo = v->blk_post_off + h.blk_base + l;
+        for (uint32_t b = 0; b < h.n_blk; ++b) max_block_docs = std::max(max_block_docs, bo[b + 1] - bo[b]);
+    }
+    ix->max_blocks = max_blocks;
+    ix->max_block_docs = max_block_docs;
+    if (int rc = upload(ix->lists, hdr.data(), dim, st, &total)) return rc;
+    if (int rc = upload(ix->postings, v->postings, P, st, &total)) return rc;
+    if (P) {
+        k_translate_postings<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
+            d_fwd_off.as<uint64_t>(), ix->rec_start.as<uint32_t>(), N, ix->postings.as<uint64_t>(), P);
+        CK(cudaGetLastError());
+    }
+    if (int rc = upload(ix->blk_post_off, v->blk_post_off, TB + dim, st, &total)) return rc;
+    if (int rc = upload(ix->blk_min, v->blk_min, TB, st, &total)) return rc;
+    if (int rc = upload(ix->blk_quant, v->blk_quant, TB, st, &total)) return rc;
+    if (int rc = upload(ix->sc_comp, v->sc_comp, TSC, st, &total)) return rc;
+    if (int rc = upload(ix->sc_run_off, v->sc_run_off, TSC + dim, st, &total)) return rc;
+    if (int rc = upload(ix->ent_blk, v->ent_blk, TE, st, &total)) return rc;
+    if (int rc = upload(ix->ent_code, v->ent_code, TE, st, &total)) return rc;
+    CK(cudaStreamSynchronize(st));
+    ix->image_bytes = total;
+    DevIndex& d = ix->ix;
+    d.lists = ix->lists.as<ListHdr>();
+    d.postings = ix->postings.as<uint64_t>();
+    d.blk_post_off = ix->blk_post_off.as<uint32_t>();
+    d.blk_min = ix->blk_min.as<float>();
+    d.blk_quant = ix->blk_quant.as<float>();
+    d.sc_comp = ix->sc_comp.as<uint32_t>();
+    d.sc_run_off = ix->sc_run_off.as<uint32_t>();
+    d.ent_blk = ix->ent_blk.as<uint16_t>();
+    d.ent_code = ix->ent_code.as<uint8_t>();
+    d.fwd = ix->fwd.as<uint4>();
+    d.rec_start = ix->rec_start.as<uint32_t>();
+    d.n_docs = N;
+    d.dim = (uint32_t)dim;
+    *out = ix.release();
+    return SGPU_OK;
+}
+
+// Device-resident batch search. All pointers are device pointers on ix->device.
+int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchParams* p, uint64_t* d_ids,
+                       float* d_scores, uint32_t* d_counts, SgpuSearchStats* stats) {
+    if (!ix || !dq || !p || !d_ids || !d_scores || !d_counts) {
+        shost::set_error("sgpu_batch_search: null argument");
+        return SGPU_EINVAL;
+    }
+    if (p->k == 0) {
+        shost::set_error("k must be > 0 (KHeap::new asserts k > 0)");
+        return SGPU_EINVAL;
+    }
+    if (p->k > 1024) {
+        shost::set_error("k > 1024 is not supported");
+        return SGPU_EUNSUPPORTED;
+    }
+    if (p->n_knn != 0) {
+        shost::set_error("n_knn > 0 (Knn::refine) is not implemented in this release");
+        return SGPU_EUNSUPPORTED;
+    }
+    if (dq->n_queries >= (1ull << 31)) {
+        shost::set_error("too many queries in one batch");
+        return SGPU_EINVAL;
+    }
+    CK(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const uint32_t nq = (uint32_t)dq->n_queries;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nq == 0) return SGPU_OK;
+    const uint32_t k = p->k;
+    uint32_t launches = 0;
+
+    CK(ix->d_nterms.ensure((size_t)nq * 4));
+    CK(ix->d_status.ensure((size_t)nq * 4));
+    CK(ix->d_counters.ensure(16));
+    CK(ix->d_stats.ensure(4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ix->d_counters.p, 0, 16, st));
+    CK(cudaMemsetAsync(ix->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
+
+    CK(cudaEventRecord(ix->ev[0], st));
+    Batch all{dq->offsets, dq->comps, dq->values, nq, 0};
+    k_prep<<<(nq + 3) / 4, 128, 0, st>>>(all, ix->ix.dim, p->query_cut, ix->d_nterms.as<uint32_t>(),
+                                         ix->d_status.as<uint32_t>(), ix->d_counters.as<uint32_t>());
+    CK(cudaGetLastError());
+    ++launches;
+    uint32_t h_counters[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_counters, ix->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_counters[2] != 0) {
+        shost::set_error("Query components must be sorted in ascending order and be < dim (" +
+                         std::to_string(h_counters[2]) + " invalid queries)");
+        return SGPU_EINVAL;
+    }
+    CK(cudaEventRecord(ix->ev[1], st));
+    const uint32_t cut_eff = std::max(1u, h_counters[1]);
+    const uint32_t est_stride = std::max(32u, (ix->max_blocks + 31u) & ~31u);
+    // chunk the batch so that the estimate scratch stays within budget
+    const uint64_t per_query = (uint64_t)cut_eff * est_stride * 4 + (uint64_t)est_stride * 2 + (uint64_t)cut_eff * 4 +
+                               (uint64_t)k * 4;
+    uint32_t chunk = (uint32_t)std::min<uint64_t>(nq, std::max<uint64_t>(1, ix->scratch_bytes / per_query));
+    CK(ix->d_terms.ensure((size_t)chunk * cut_eff * 4));
+    CK(ix->d_est.ensure((size_t)chunk * cut_eff * est_stride * 4));
+    CK(ix->d_order.ensure((size_t)chunk * est_stride * 2));
+    CK(ix->d_keys.ensure((size_t)chunk * k * 4));
+
+    // shared memory plan of k_search
+    SearchArgs a{};
+    a.ix = ix->ix;
+    a.k = k;
+    a.heap_factor = p->heap_factor;
+    a.first_sorted = p->first_sorted ? 1 : 0;
+    a.wave_docs = std::max(1u, ix->wave_docs);
+    a.first_wave_docs = std::max(1u, ix->first_wave_docs);
+    a.buf_docs = std::max(std::max(a.wave_docs, a.first_wave_docs), std::max(1u, ix->max_block_docs));
+    a.qd_words = (ix->ix.dim + 31u) & ~31u;
+    const size_t fixed = (size_t)a.qd_words * 4 + 3 * SEARCH_THREADS * 4 + 2 * (size_t)((k + 3) & ~3u) * 4;
+    size_t smem = fixed + (size_t)a.buf_docs * 12;
+    const int ctas = std::max(1, ix->ctas);
+    if (fixed + 1024 > ix->smem_optin) {
+        shost::set_error("dense query does not fit in shared memory (use the large-vocabulary path)");
+        return SGPU_EUNSUPPORTED;
+    }
+    if (smem + 1024 > ix->smem_optin) {  // wave buffers spill to global scratch
+        CK(ix->d_gdocs.ensure((size_t)ctas * a.buf_docs * 8));
+        CK(ix->d_gscores.ensure((size_t)ctas * a.buf_docs * 4));
+        a.g_docs = ix->d_gdocs.as<uint64_t>();
+        a.g_scores = ix->d_gscores.as<float>();
+        smem = fixed;
+    }
+    CK(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    float ms_sum = 0.f, ms_search = 0.f, ms_fin = 0.f, ms_terms = 0.f;
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t n = std::min(chunk, nq - q0);
+        Batch b{dq->offsets, dq->comps, dq->values, n, q0};
+        Scratch sc{};
+        sc.terms = ix->d_terms.as<uint32_t>();
+        sc.nterms = ix->d_nterms.as<uint32_t>() + q0;
+        sc.status = ix->d_status.as<uint32_t>() + q0;
+        sc.est = ix->d_est.as<float>();
+        sc.order = ix->d_order.as<uint16_t>();
+        sc.counters = ix->d_counters.as<uint32_t>();
+        sc.out_keys = ix->d_keys.as<uint32_t>();
+        sc.stats = ix->d_stats.as<unsigned long long>();
+        sc.est_stride = est_stride;
+        sc.cut_eff = cut_eff;
+        CK(cudaEventRecord(ix->ev[2], st));
+        k_terms<<<(n + 3) / 4, 128, 0, st>>>(b, sc.nterms, cut_eff, sc.terms);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ix->ev[3], st));
+        const uint64_t tasks = (uint64_t)n * cut_eff;
+        k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);
+        CK(cudaGetLastError());
+        launches += 2;
+        if (a.first_sorted) {
+            k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        CK(cudaMemsetAsync(ix->d_counters.p, 0, 4, st));
+        CK(cudaEventRecord(ix->ev[4], st));
+        a.b = b;
+        a.sc = sc;
+        a.out_scores = d_scores + (uint64_t)q0 * k;
+        a.out_counts = d_counts + q0;
+        k_search<<<ctas, SEARCH_THREADS, smem, st>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ix->ev[5], st));
+        const uint64_t tot = (uint64_t)n * k;
+        k_finish<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->ix.rec_start, ix->ix.n_docs, sc.out_keys,
+                                                                a.out_counts, k, n, d_ids + (uint64_t)q0 * k);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ix->ev[6], st));
+        launches += 2;
+        CK(cudaStreamSynchronize(st));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3])); ms_terms += ms;
+        CK(cudaEventElapsedTime(&ms, ix->ev[3], ix->ev[4])); ms_sum += ms;
+        CK(cudaEventElapsedTime(&ms, ix->ev[4], ix->ev[5])); ms_search += ms;
+        CK(cudaEventElapsedTime(&ms, ix->ev[5], ix->ev[6])); ms_fin += ms;
+    }
+    if (stats) {
+        float ms_prep = 0.f;
+        CK(cudaEventElapsedTime(&ms_prep, ix->ev[0], ix->ev[1]));
+        unsigned long long hs[4];
+        CK(cudaMemcpy(hs, ix->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost));
+        stats->ms_prep = ms_prep + ms_terms;
+        stats->ms_summary = ms_sum;
+        stats->ms_search = ms_search;
+        stats->ms_finish = ms_fin;
+        stats->ms_total = stats->ms_prep + ms_sum + ms_search + ms_fin;
+        stats->n_launches = launches;
+        stats->docs_scored = hs[0];
+        stats->blocks_scored = hs[1];
+        stats->blocks_pushed = hs[2];
+        stats->fwd_bytes = hs[3] * 32ull;
+    }
+    return SGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgpu_index_create(const SgpuIndexView* view, int device, SgpuIndex** out) {
+    try {
+        return create_impl(view, device, out);
+    } catch (const std::bad_alloc&) {
+        shost::set_error("out of host memory");
+        return SGPU_ENOMEM;
+    }
+}
+
+void sgpu_index_destroy(SgpuIndex* index) { delete index; }
+
+uint64_t sgpu_index_device_bytes(const SgpuIndex* index) { return index ? index->image_bytes : 0; }
+
+int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
+    if (!ix || !name) return SGPU_EINVAL;
+    std::string n(name);
+    if (value <= 0) {
+        shost::set_error("option values must be positive");
+        return SGPU_EINVAL;
+    }
+    if (n == "wave_docs") ix->wave_docs = (uint32_t)value;
+    else if (n == "first_wave_docs") ix->first_wave_docs = (uint32_t)value;
+    else if (n == "ctas") ix->ctas = (int)value;
+    else if (n == "scratch_mb") ix->scratch_bytes = (uint64_t)value << 20;
+    else {
+        shost::set_error("unknown option: " + n);
+        return SGPU_EINVAL;
+    }
+    return SGPU_OK;
+}
+
+int sgpu_batch_search_device(SgpuIndex* index, const SgpuQueryBatch* d_queries, const SgpuSearchParams* params,
+                             uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts,
+                             SgpuSearchStats* stats) {
+    return search_device_impl(index, d_queries, params, d_out_ids, d_out_scores, d_out_counts, stats);
+}
+
+int sgpu_batch_search(SgpuIndex* ix, const SgpuQueryBatch* q, const SgpuSearchParams* p, uint64_t* out_ids,
+                      float* out_scores, uint32_t* out_counts, SgpuSearchStats* stats) {
+    if (!ix || !q || !p || !out_ids || !out_scores || !out_counts) {
+        shost::set_error("sgpu_batch_search: null argument");
+        return SGPU_EINVAL;
+    }
+    if (p->k == 0) {
+        shost::set_error("k must be > 0 (KHeap::new asserts k > 0)");
+        return SGPU_EINVAL;
+    }
+    CK(cudaSetDevice(ix->device));
+    const uint64_t nq = q->n_queries;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nq == 0) return SGPU_OK;
+    const uint64_t nnz = q->offsets[nq];
+    cudaStream_t st = ix->stream;
+    // stage inputs through pinned memory so the copies are truly asynchronous DMA
+    const size_t b_off = (nq + 1) * 8, b_c = nnz * 4, b_v = nnz * 4;
+    CK(ix->h_in.ensure(b_off + b_c + b_v));
+    uint8_t* hin = ix->h_in.as<uint8_t>();
+    std::memcpy(hin, q->offsets, b_off);
+    if (nnz) {
+        std::memcpy(hin + b_off, q->comps, b_c);
+        std::memcpy(hin + b_off + b_c, q->values, b_v);
+    }
+    CK(ix->d_qoff.ensure(b_off));
+    CK(ix->d_qcomps.ensure(std::max<size_t>(b_c, 4)));
+    CK(ix->d_qvals.ensure(std::max<size_t>(b_v, 4)));
+    CK(cudaMemcpyAsync(ix->d_qoff.p, hin, b_off, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CK(cudaMemcpyAsync(ix->d_qcomps.p, hin + b_off, b_c, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_qvals.p, hin + b_off + b_c, b_v, cudaMemcpyHostToDevice, st));
+    }
+    const size_t o_ids = nq * p->k * 8, o_sc = nq * p->k * 4, o_cnt = nq * 4;
+    CK(ix->d_out_ids.ensure(o_ids));
+    CK(ix->d_out_scores.ensure(o_sc));
+    CK(ix->d_out_counts.ensure(o_cnt));
+    SgpuQueryBatch dq{nq, ix->d_qoff.as<uint64_t>(), ix->d_qcomps.as<uint32_t>(), ix->d_qvals.as<float>()};
+    int rc = search_device_impl(ix, &dq, p, ix->d_out_ids.as<uint64_t>(), ix->d_out_scores.as<float>(),
+                                ix->d_out_counts.as<uint32_t>(), stats);
+    if (rc != SGPU_OK) return rc;
+    CK(ix->h_out.ensure(o_ids + o_sc + o_cnt));
+    uint8_t* hout = ix->h_out.as<uint8_t>();
+    CK(cudaMemcpyAsync(hout, ix->d_out_ids.p, o_ids, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hout + o_ids, ix->d_out_scores.p, o_sc, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hout + o_ids + o_sc, ix->d_out_counts.p, o_cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(out_ids, hout, o_ids);
+    std::memcpy(out_scores, hout + o_ids, o_sc);
+    std::memcpy(out_counts, hout + o_ids + o_sc, o_cnt);
+    return SGPU_OK;
+}
+
+int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64_t* out_ids, float* out_scores,
+                      uint32_t* out_counts, float* ms_kernel) {
+    if (!ix || !q || !out_ids || !out_scores || !out_counts || k == 0 || k > 1024) {
+        shost::set_error("sgpu_exact_search: bad argument");
+        return SGPU_EINVAL;
+    }
+    CK(cudaSetDevice(ix->device));
+    const uint64_t nq = q->n_queries;
+    if (nq == 0) return SGPU_OK;
+    const uint64_t nnz = q->offsets[nq];
+    cudaStream_t st = ix->stream;
+    for (uint64_t i = 0; i < nq; ++i)
+        for (uint64_t j = q->offsets[i]; j < q->offsets[i + 1]; ++j)
+            if (q->comps[j] >= ix->ix.dim || (j > q->offsets[i] && q->comps[j] < q->comps[j - 1])) {
+                shost::set_error("Query components must be sorted in ascending order and be < dim");
+                return SGPU_EINVAL;
+            }
+    CK(ix->d_qoff.ensure((nq + 1) * 8));
+    CK(ix->d_qcomps.ensure(std::max<size_t>(nnz * 4, 4)));
+    CK(ix->d_qvals.ensure(std::max<size_t>(nnz * 4, 4)));
+    CK(cudaMemcpyAsync(ix->d_qoff.p, q->offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CK(cudaMemcpyAsync(ix->d_qcomps.p, q->comps, nnz * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_qvals.p, q->values, nnz * 4, cudaMemcpyHostToDevice, st));
+    }
+    CK(ix->d_out_ids.ensure(nq * k * 8));
+    CK(ix->d_out_scores.ensure(nq * k * 4));
+    CK(ix->d_out_counts.ensure(nq * 4));
+    // segments sized to stay L2 resident while many queries stream over them
+    const uint64_t N = ix->ix.n_docs;
+    const uint32_t seg_docs = 131072;
+    const uint32_t n_seg = (uint32_t)std::max<uint64_t>(1, (N + seg_docs - 1) / seg_docs);
+    DevBuf part_keys, part_scores;
+    CK(part_keys.ensure((size_t)nq * n_seg * k * 4));
+    CK(part_scores.ensure((size_t)nq * n_seg * k * 4));
+    ExactArgs ea{};
+    ea.fwd = ix->ix.fwd;
+    ea.rec_start = ix->ix.rec_start;
+    ea.n_docs = N;
+    ea.q_off = ix->d_qoff.as<uint64_t>();
+    ea.q_comps = ix->d_qcomps.as<uint32_t>();
+    ea.q_vals = ix->d_qvals.as<float>();
+    ea.nq = (uint32_t)nq;
+    ea.k = k;
+    ea.seg_docs = seg_docs;
+    ea.n_seg = n_seg;
+    ea.qd_words = (ix->ix.dim + 31u) & ~31u;
+    ea.part_keys = part_keys.as<uint32_t>();
+    ea.part_scores = part_scores.as<float>();
+    const size_t smem = (size_t)ea.qd_words * 4 + 2 * (size_t)((k + 3) & ~3u) * 4 + EXACT_CAND * 8;
+    if (smem + 1024 > ix->smem_optin) {
+        shost::set_error("dense query does not fit in shared memory");
+        return SGPU_EUNSUPPORTED;
+    }
+    CK(cudaFuncSetAttribute(k_exact_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaEventRecord(ix->ev[0], st));
+    const uint64_t n_cta = (uint64_t)nq * n_seg;
+    k_exact_partial<<<(unsigned)n_cta, EXACT_THREADS, smem, st>>>(ea);
+    CK(cudaGetLastError());
+    k_exact_merge<<<(unsigned)nq, 32, 2 * (size_t)((k + 3) & ~3u) * 4, st>>>(
+        ea, nullptr, ix->d_out_scores.as<float>(), ix->d_out_counts.as<uint32_t>(),
+        ix->d_out_ids.as<uint64_t>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ix->ev[1], st));
+    CK(cudaMemcpyAsync(out_ids, ix->d_out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_scores, ix->d_out_scores.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_counts, ix->d_out_counts.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms_kernel) CK(cudaEventElapsedTime(ms_kernel, ix->ev[0], ix->ev[1]));
+    return SGPU_OK;
+}
+
+const char* sgpu_version(void) { return "seismic_b200 0.1.0 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/seismic_b200.h declares (no compute calls)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+
+
+def declared_symbols():
+    text = (REPO / "include" / "seismic_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:sgpu|shost)_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(native):
+    lib = ctypes.CDLL(str(native.LIB_PATH))
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_bindings_cover_header(native):
+    assert set(declared_symbols()) == set(native.SYMBOLS)
+
+
+def test_version_and_defaults(native):
+    lib = native.lib()
+    assert b"sm_100a" in lib.sgpu_version()
+    cfg = native.BuildConfig()
+    lib.shost_default_config(ctypes.byref(cfg))
+    # Python defaults of the reference, src/pylib/mod.rs:329
+    assert (cfg.n_postings, cfg.min_cluster_size, cfg.doc_cut) == (3500, 2, 15)
+    assert abs(cfg.centroid_fraction - 0.1) < 1e-7 and abs(cfg.summary_energy - 0.4) < 1e-7
+    assert abs(cfg.max_fraction - 1.5) < 1e-7
+    assert ctypes.sizeof(native.BuildConfig) == 64
+
+
+def test_struct_layouts_match_header(native):
+    # sizes the C compiler gives these structs (x86-64 SysV): guards against binding drift
+    assert ctypes.sizeof(native.IndexView) == 32 + 16 * 8
+    assert ctypes.sizeof(native.QueryBatch) == 32
+    assert ctypes.sizeof(native.SearchParams) == 20
+    assert ctypes.sizeof(native.SearchStats) == 28 + 4 + 32
+    assert ctypes.sizeof(native.SynthConfig) == 56
+
+
+def test_no_gpu_fails_loudly(native, synth_small):
+    """Without a CUDA device the product path must raise, never fall back to a CPU implementation."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from seismic_b200 import GpuIndex
+    _, _, index = synth_small
+    with pytest.raises(native.SeismicError):
+        GpuIndex(index, 0)
+
+
+def test_product_never_imports_oracle():
+    for p in (REPO / "seismic_b200").rglob("*"):
+        if p.suffix in {".py", ".cpp", ".hpp", ".cu", ".cuh", ".h"}:
+            text = p.read_text()
+            assert "import oracle" not in text and "from oracle" not in text and "oracle_search" not in text, p
+            assert "liboracle" not in text, p

@@ -1,0 +1,180 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same index and
+queries.  Bar: identical doc ids, bit-identical f32 scores (the kernel and the oracle use the same summation
+order), identical counts.  Run with `pytest -m gpu` on the B200 box."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from seismic_b200 import Dataset, GpuIndex, HostIndex, recall_at_k
+from seismic_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+GOLD = json.loads((Path(__file__).parent / "golden" / "reference_known_answers.json").read_text())
+
+
+def assert_same(gpu, ref, what=""):
+    gi, gs, gc = gpu[:3]
+    ri, rs, rc = ref[:3]
+    assert (gc == rc).all(), f"{what}: counts differ for {int((gc != rc).sum())} queries"
+    bad = np.nonzero((gi != ri).any(axis=1))[0]
+    assert len(bad) == 0, f"{what}: ids differ for {len(bad)} queries, first {bad[:5]}: {gi[bad[0]]} vs {ri[bad[0]]}"
+    assert (gs.view(np.uint32) == rs.view(np.uint32)).all() or np.array_equal(gs, rs), f"{what}: scores differ"
+
+
+@pytest.fixture(scope="module")
+def gpu_small(synth_small):
+    return GpuIndex(synth_small[2], 0)
+
+
+@pytest.fixture(scope="module")
+def gpu_pruned(synth_pruned):
+    return GpuIndex(synth_pruned[2], 0)
+
+
+@pytest.mark.parametrize("k,cut,hf,srt", [
+    (10, 3, 0.8, True), (10, 3, 0.8, False), (10, 1, 0.9, True), (10, 10, 1.0, True), (1, 3, 0.8, True),
+    (100, 5, 0.7, True), (33, 4, 0.0, False), (10, 1000, 0.8, True)])
+def test_parity_small(oracle_mod, synth_small, gpu_small, k, cut, hf, srt):
+    _, q, index = synth_small
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    got = gpu_small.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    assert_same(got, ref, f"k={k} cut={cut} hf={hf} sorted={srt}")
+    assert gpu_small.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
+@pytest.mark.parametrize("k,cut,hf,srt", [(10, 3, 0.8, True), (10, 3, 0.8, False), (100, 8, 0.9, True), (10, 3, 1.2, True)])
+def test_parity_pruned(oracle_mod, synth_pruned, gpu_pruned, k, cut, hf, srt):
+    _, q, index = synth_pruned
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    got = gpu_pruned.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    assert_same(got, ref, f"k={k} cut={cut} hf={hf} sorted={srt}")
+    assert gpu_pruned.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+    assert gpu_pruned.last_stats["docs_scored"] >= ref[3]["docs_scored"]
+
+
+@pytest.mark.parametrize("wave,first", [(1, 1), (64, 8), (512, 512), (4096, 4096)])
+def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first):
+    """The speculative wave scheduler is a performance knob only: any wave size replays to the same heap."""
+    _, q, index = synth_pruned
+    g = GpuIndex(index, 0)
+    g.set_option("wave_docs", wave)
+    g.set_option("first_wave_docs", first)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 3, 0.8, first_sorted=True)
+    got = g.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8, first_sorted=True)
+    assert_same(got, ref, f"wave={wave}")
+
+
+def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
+    _, q, index = synth_small
+    g = GpuIndex(index, 0)
+    g.set_option("scratch_mb", 1)
+    g.set_option("ctas", 7)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 3, 0.8)
+    got = g.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8)
+    assert_same(got, ref, "chunked")
+
+
+@pytest.mark.parametrize("name", ["test_empty_vectors", "rust_usage_example"])
+def test_reference_known_answers_on_gpu(name):
+    case = GOLD[name]
+    comps = [np.array(c, dtype=np.uint32) for c, _ in case["docs"]]
+    vals = [np.array(v, dtype=np.float32) for _, v in case["docs"]]
+    index = HostIndex.build(Dataset.from_lists(comps, vals, dim=case["dim"]))
+    g = GpuIndex(index, 0)
+    qc = np.array(case["query"][0], np.uint32)
+    qv = np.array(case["query"][1], np.float32)
+    ids, scores, counts = g.batch_search(np.array([0, len(qc)], np.uint64), qc, qv, case["k"], case["query_cut"],
+                                         case["heap_factor"], first_sorted=case["first_sorted"])
+    n = int(counts[0])
+    assert ids[0, :n].tolist() == case["expected_ids"]
+    assert scores[0, :n].tolist() == case["expected_scores"]
+    assert (ids[0, n:] == N.PAD_ID).all() and np.isneginf(scores[0, n:]).all()
+
+
+def test_edge_queries(oracle_mod, synth_pruned, gpu_pruned):
+    """Empty query, single-term query, repeated components, a query made of one whole document, ragged batch."""
+    docs, q, index = synth_pruned
+    dc, dv = docs.vector(17)
+    comps = [np.empty(0, np.uint32), np.array([5], np.uint32), np.array([7, 7, 9, 9, 9, 400], np.uint32),
+             dc.copy(), np.arange(0, 2000, 7, dtype=np.uint32)]
+    vals = [np.empty(0, np.float32), np.array([1.5], np.float32), np.array([0.5, 2.0, 1.0, 3.0, 0.1, 0.7], np.float32),
+            dv.copy(), np.linspace(0.01, 2.0, len(comps[4]), dtype=np.float32)]
+    off = np.zeros(len(comps) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in comps])
+    qc, qv = np.concatenate(comps), np.concatenate(vals)
+    for srt in (True, False):
+        ref = oracle_mod.batch_search(index.view, off, qc, qv, 10, 3, 0.8, first_sorted=srt)
+        got = gpu_pruned.batch_search(off, qc, qv, 10, 3, 0.8, first_sorted=srt)
+        assert_same(got, ref, f"edge sorted={srt}")
+        assert got[2][0] == 0 and (got[0][0] == N.PAD_ID).all()
+        assert got[0][3, 0] == 17        # a document used as query retrieves itself first
+
+
+def test_empty_batch_and_errors(synth_pruned, gpu_pruned):
+    _, q, index = synth_pruned
+    ids, scores, counts = gpu_pruned.batch_search(np.zeros(1, np.uint64), np.empty(0, np.uint32), np.empty(0, np.float32), 10, 3, 0.8)
+    assert ids.shape == (0, 10) and counts.shape == (0,)
+    off = np.array([0, 2], np.uint64)
+    with pytest.raises(ValueError):
+        gpu_pruned.batch_search(off, np.array([9, 3], np.uint32), np.ones(2, np.float32), 10, 3, 0.8)
+    with pytest.raises(ValueError):
+        gpu_pruned.batch_search(off, np.array([3, index.dim], np.uint32), np.ones(2, np.float32), 10, 3, 0.8)
+    with pytest.raises(ValueError):
+        gpu_pruned.batch_search(off, np.array([3, 9], np.uint32), np.ones(2, np.float32), 0, 3, 0.8)
+    with pytest.raises(NotImplementedError):
+        gpu_pruned.batch_search(off, np.array([3, 9], np.uint32), np.ones(2, np.float32), 10, 3, 0.8, n_knn=5)
+    # the index stays usable after an error
+    got = gpu_pruned.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8)
+    assert got[2].max() == 10
+
+
+def test_exact_search_matches_oracle(oracle_mod, synth_pruned, gpu_pruned):
+    _, q, index = synth_pruned
+    n = 64
+    off = q.offsets[: n + 1].copy()
+    qc, qv = q.comps[: int(off[-1])], q.values[: int(off[-1])]
+    ref = oracle_mod.exact_search(index.view, off, qc, qv, 10)
+    got = gpu_pruned.exact_search(off, qc, qv, 10)
+    assert_same(got, ref, "exact")
+    approx = gpu_pruned.batch_search(off, qc, qv, 10, 3, 0.8)
+    r = recall_at_k(got[0], got[2], approx[0], approx[2])
+    assert 0.5 < r <= 1.0
+
+
+def test_device_pointer_entry(oracle_mod, synth_pruned, gpu_pruned):
+    """sgpu_batch_search_device with torch-owned device buffers (what the NCCL gather path uses)."""
+    import torch
+    _, q, index = synth_pruned
+    dev = torch.device("cuda:0")
+    d_off = torch.from_numpy(q.offsets.astype(np.int64)).to(dev)
+    d_c = torch.from_numpy(q.comps.astype(np.int32)).to(dev)
+    d_v = torch.from_numpy(q.values.copy()).to(dev)
+    nq, k = len(q), 10
+    d_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    d_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    st = gpu_pruned.batch_search_device(d_off.data_ptr(), d_c.data_ptr(), d_v.data_ptr(), nq, k, 3, 0.8,
+                                        d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr())
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, 3, 0.8)
+    got = (d_ids.cpu().numpy().view(np.uint64), d_sc.cpu().numpy(), d_cnt.cpu().numpy().view(np.uint32))
+    assert_same(got, ref, "device entry")
+    assert st["n_launches"] >= 5 and st["ms_search"] > 0
+
+
+def test_full_scan_equals_exact(synth_pruned, gpu_pruned):
+    """Property: with heap_factor = 0 nothing is skipped, so searching ALL query terms returns the exact top-k
+    among documents that share a pruned posting with the query — and every returned score is the true dot."""
+    docs, q, index = synth_pruned
+    n = 32
+    off = q.offsets[: n + 1].copy()
+    qc, qv = q.comps[: int(off[-1])], q.values[: int(off[-1])]
+    ids, scores, counts = gpu_pruned.batch_search(off, qc, qv, 10, 10000, 0.0, first_sorted=False)
+    for i in range(n):
+        dense = np.zeros(index.dim, np.float32)
+        dense[qc[int(off[i]):int(off[i + 1])]] = qv[int(off[i]):int(off[i + 1])]
+        for r in range(int(counts[i])):
+            c, v = index.get_doc(int(ids[i, r]))
+            assert abs(float(np.dot(dense[c].astype(np.float64), v.astype(np.float64))) - scores[i, r]) <= 1e-4 * max(1.0, abs(scores[i, r]))
