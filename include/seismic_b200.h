@@ -158,6 +158,10 @@ int sgpu_batch_search_device(SgpuIndex* index, const SgpuQueryBatch* d_queries, 
                              uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_counts,
                              SgpuSearchStats* stats);
 
+/* Enqueue all work of this index on `cuda_stream` (a cudaStream_t of the index's device, e.g. the caller's
+ * torch stream) instead of the library's private stream; NULL restores the private stream. */
+int sgpu_index_set_stream(SgpuIndex* index, void* cuda_stream);
+
 /* Tuning knobs (do not change results): wave sizes of the speculative block scheduler, CTA count.
  * name in {"wave_docs","first_wave_docs","ctas","scratch_mb"}; returns SGPU_EINVAL for unknown. */
 int sgpu_index_set_option(SgpuIndex* index, const char* name, int64_t value);

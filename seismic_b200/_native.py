@@ -114,6 +114,7 @@ SYMBOLS = {
                                     C.c_void_p, C.c_void_p, C.POINTER(SearchStats)]),
     "sgpu_batch_search_device": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.POINTER(SearchParams), C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.POINTER(SearchStats)]),
+    "sgpu_index_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgpu_index_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "sgpu_exact_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_float)]),

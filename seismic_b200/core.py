@@ -229,6 +229,10 @@ class GpuIndex:
     def device_bytes(self) -> int:
         return int(N.lib().sgpu_index_device_bytes(self._h))
 
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = private stream."""
+        N.check(N.lib().sgpu_index_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     def set_option(self, name: str, value: int) -> None:
         N.check(N.lib().sgpu_index_set_option(self._h, name.encode(), int(value)))
 

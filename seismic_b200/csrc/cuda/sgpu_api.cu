@@ -74,7 +74,8 @@ struct SgpuIndex {
     int device = 0;
     int n_sm = 0;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream all work is enqueued on
+    cudaStream_t own_stream = nullptr;  // the library's private stream
     cudaEvent_t ev[8] = {};
     // image
     DevBuf lists, postings, blk_post_off, blk_min, blk_quant, sc_comp, sc_run_off, ent_blk, ent_code, fwd, rec_start;
@@ -94,7 +95,7 @@ struct SgpuIndex {
         cudaSetDevice(device);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
+        if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
 
@@ -138,7 +139,8 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     ix->smem_optin = (size_t)optin;
     ix->ctas = ix->n_sm;
-    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+    ix->stream = ix->own_stream;
     for (auto& e : ix->ev) CK(cudaEventCreate(&e));
     cudaStream_t st = ix->stream;
     const uint64_t N = v->n_docs, dim = v->dim;
@@ -428,6 +430,12 @@ int sgpu_index_create(const SgpuIndexView* view, int device, SgpuIndex** out) {
 void sgpu_index_destroy(SgpuIndex* index) { delete index; }
 
 uint64_t sgpu_index_device_bytes(const SgpuIndex* index) { return index ? index->image_bytes : 0; }
+
+int sgpu_index_set_stream(SgpuIndex* ix, void* cuda_stream) {
+    if (!ix) return SGPU_EINVAL;
+    ix->stream = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
+    return SGPU_OK;
+}
 
 int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     if (!ix || !name) return SGPU_EINVAL;
