@@ -6,7 +6,7 @@
 // Grid: one CTA per (segment, query), segment-major, so the CTAs resident at one time stream the SAME
 // ~60 MB slice of the record buffer for different queries and the slice is served from the 126 MB L2.
 #pragma once
-#include "kernels.cuh"
+#include "search.cuh"
 
 namespace sgpu {
 
@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
         if (i + 1 == qn || a.q_comps[qo + i + 1] != c) qd[c] = a.q_vals[qo + i];
     }
     __syncthreads();
+    DenseQuery dq;
+    dq.qd = qd;
     uint32_t heap_n = 0, wkey = 0, widx = 0;
     float theta = 0.f;
     const uint64_t d_lo = (uint64_t)seg * a.seg_docs;
@@ -60,10 +62,7 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
             r0 = __ldg(a.rec_start + d);
             nch = __ldg(a.rec_start + d + 1) - r0;
         }
-        float s = score_rec(a.fwd + (uint64_t)r0 * 2, nch, lane8, qd);
-        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 4));
-        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));
-        s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
+        float s = group_reduce(score_rec(a.fwd + (uint64_t)r0 * 2, nch, lane8, dq));
         if (lane8 == 0 && nch > 0 && (!s_full || better(s, r0, s_theta, s_wkey))) {
             const uint32_t slot = atomicAdd(&s_ncand, 1u);
             cand_s[slot] = s;

@@ -11,6 +11,7 @@
 #include "../../../include/seismic_b200.h"
 #include "exact.cuh"
 #include "kernels.cuh"
+#include "search.cuh"
 
 namespace shost {
 void set_error(const std::string& msg);
@@ -84,12 +85,14 @@ struct SgpuIndex {
     uint32_t max_blocks = 0;      // largest number of blocks of any list
     uint32_t max_block_docs = 0;  // largest block
     // options
-    uint32_t wave_docs = 2048, first_wave_docs = 256;
+    uint32_t wave_docs = 2048, first_wave_docs = 256;       // dense-query kernel (1024 threads)
+    uint32_t hq_wave_docs = 384, hq_first_wave_docs = 64;  // hash-query kernel (128 threads)
+    int hq_enabled = 1, hq_ctas_per_sm = 0;
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
     // per-batch scratch (grow-only)
     DevBuf d_qoff, d_qcomps, d_qvals, d_nterms, d_status, d_counters, d_terms, d_est, d_order, d_keys, d_stats;
-    DevBuf d_out_ids, d_out_scores, d_out_counts, d_gdocs, d_gscores;
+    DevBuf d_out_ids, d_out_scores, d_out_counts, d_gdocs, d_gscores, d_hmult, d_qlist;
     PinnedBuf h_in, h_out;
     ~SgpuIndex() {
         cudaSetDevice(device);
@@ -288,9 +291,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
 
     CK(ix->d_nterms.ensure((size_t)nq * 4));
     CK(ix->d_status.ensure((size_t)nq * 4));
-    CK(ix->d_counters.ensure(16));
+    CK(ix->d_counters.ensure(32));
     CK(ix->d_stats.ensure(4 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ix->d_counters.p, 0, 16, st));
+    CK(cudaMemsetAsync(ix->d_counters.p, 0, 32, st));
     CK(cudaMemsetAsync(ix->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
 
     CK(cudaEventRecord(ix->ev[0], st));
@@ -312,38 +315,67 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     const uint32_t est_stride = std::max(32u, (ix->max_blocks + 31u) & ~31u);
     // chunk the batch so that the estimate scratch stays within budget
     const uint64_t per_query = (uint64_t)cut_eff * est_stride * 4 + (uint64_t)est_stride * 2 + (uint64_t)cut_eff * 4 +
-                               (uint64_t)k * 4;
+                               (uint64_t)k * 4 + 12;
     uint32_t chunk = (uint32_t)std::min<uint64_t>(nq, std::max<uint64_t>(1, ix->scratch_bytes / per_query));
     CK(ix->d_terms.ensure((size_t)chunk * cut_eff * 4));
     CK(ix->d_est.ensure((size_t)chunk * cut_eff * est_stride * 4));
     CK(ix->d_order.ensure((size_t)chunk * est_stride * 2));
     CK(ix->d_keys.ensure((size_t)chunk * k * 4));
+    CK(ix->d_hmult.ensure((size_t)chunk * 4));
+    CK(ix->d_qlist.ensure((size_t)chunk * 8));
 
-    // shared memory plan of k_search
-    SearchArgs a{};
-    a.ix = ix->ix;
-    a.k = k;
-    a.heap_factor = p->heap_factor;
-    a.first_sorted = p->first_sorted ? 1 : 0;
-    a.wave_docs = std::max(1u, ix->wave_docs);
-    a.first_wave_docs = std::max(1u, ix->first_wave_docs);
-    a.buf_docs = std::max(std::max(a.wave_docs, a.first_wave_docs), std::max(1u, ix->max_block_docs));
-    a.qd_words = (ix->ix.dim + 31u) & ~31u;
-    const size_t fixed = (size_t)a.qd_words * 4 + 3 * SEARCH_THREADS * 4 + 2 * (size_t)((k + 3) & ~3u) * 4;
-    size_t smem = fixed + (size_t)a.buf_docs * 12;
+    // ---- launch plans of the two k_search instantiations
+    const size_t heap_bytes = 2 * (size_t)((k + 3) & ~3u) * 4;
+    SearchArgs ad{};  // dense-query kernel: 1 CTA / SM
+    ad.ix = ix->ix;
+    ad.k = k;
+    ad.heap_factor = p->heap_factor;
+    ad.first_sorted = p->first_sorted ? 1 : 0;
+    ad.wave_docs = std::max(1u, ix->wave_docs);
+    ad.first_wave_docs = std::max(1u, ix->first_wave_docs);
+    ad.buf_docs = std::max(std::max(ad.wave_docs, ad.first_wave_docs), std::max(1u, ix->max_block_docs));
+    ad.qd_words = (ix->ix.dim + 31u) & ~31u;
+    ad.counter_idx = 0;
     const int ctas = std::max(1, ix->ctas);
-    if (fixed + 1024 > ix->smem_optin) {
-        shost::set_error("dense query does not fit in shared memory (use the large-vocabulary path)");
+    const size_t fixed_d = (size_t)ad.qd_words * 4 + 3 * DENSE_THREADS * 4 + heap_bytes;
+    size_t smem_d = fixed_d + (size_t)ad.buf_docs * 12;
+    bool dense_ok = fixed_d + 1024 <= ix->smem_optin;
+    if (dense_ok && smem_d + 1024 > ix->smem_optin) {  // wave buffers spill to global scratch
+        CK(ix->d_gdocs.ensure((size_t)ctas * ad.buf_docs * 8));
+        CK(ix->d_gscores.ensure((size_t)ctas * ad.buf_docs * 4));
+        ad.g_docs = ix->d_gdocs.as<uint64_t>();
+        ad.g_scores = ix->d_gscores.as<float>();
+        smem_d = fixed_d;
+    }
+    auto kd = k_search<DENSE_THREADS, DenseQuery>;
+    auto kh = k_search<HQ_THREADS, HashQuery>;
+    if (dense_ok) CK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+
+    SearchArgs ah = ad;  // hash-query kernel: several CTAs / SM
+    ah.g_docs = nullptr;
+    ah.g_scores = nullptr;
+    ah.wave_docs = std::max(1u, ix->hq_wave_docs);
+    ah.first_wave_docs = std::max(1u, ix->hq_first_wave_docs);
+    ah.buf_docs = std::max(std::max(ah.wave_docs, ah.first_wave_docs), std::max(1u, ix->max_block_docs));
+    ah.counter_idx = 3;
+    const size_t smem_h = (size_t)HQ_SLOTS * 6 + 3 * HQ_THREADS * 4 + heap_bytes + (size_t)ah.buf_docs * 12;
+    bool hq_ok = ix->hq_enabled && smem_h + 1024 <= ix->smem_optin / 2;  // at least 2 CTAs per SM or not worth it
+    int hq_ctas = 0;
+    if (hq_ok) {
+        CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kh, HQ_THREADS, smem_h));
+        if (ix->hq_ctas_per_sm > 0) occ = std::min(occ, ix->hq_ctas_per_sm);
+        hq_ok = occ >= 1;
+        hq_ctas = occ * ix->n_sm;
+    }
+    if (!hq_ok && !dense_ok) {
+        shost::set_error("neither the hash-query nor the dense-query kernel fits this index in shared memory");
         return SGPU_EUNSUPPORTED;
     }
-    if (smem + 1024 > ix->smem_optin) {  // wave buffers spill to global scratch
-        CK(ix->d_gdocs.ensure((size_t)ctas * a.buf_docs * 8));
-        CK(ix->d_gscores.ensure((size_t)ctas * a.buf_docs * 4));
-        a.g_docs = ix->d_gdocs.as<uint64_t>();
-        a.g_scores = ix->d_gscores.as<float>();
-        smem = fixed;
-    }
-    CK(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // queries the hash path cannot take need the dense kernel
+    const uint32_t hq_max_nnz = hq_ok ? (dense_ok ? (uint32_t)HQ_MAX_NNZ : 0xffffffffu) : 0u;
+    const uint32_t hq_tries = dense_ok ? (uint32_t)HQ_TRIES : 4096u;
 
     float ms_sum = 0.f, ms_search = 0.f, ms_fin = 0.f, ms_terms = 0.f;
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -356,38 +388,53 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         sc.est = ix->d_est.as<float>();
         sc.order = ix->d_order.as<uint16_t>();
         sc.counters = ix->d_counters.as<uint32_t>();
+        sc.hmult = ix->d_hmult.as<uint32_t>();
+        sc.qlist_hq = ix->d_qlist.as<uint32_t>();
+        sc.qlist_dense = ix->d_qlist.as<uint32_t>() + chunk;
         sc.out_keys = ix->d_keys.as<uint32_t>();
         sc.stats = ix->d_stats.as<unsigned long long>();
         sc.est_stride = est_stride;
         sc.cut_eff = cut_eff;
+        CK(cudaMemsetAsync(ix->d_counters.p, 0, 32, st));
         CK(cudaEventRecord(ix->ev[2], st));
-        k_terms<<<(n + 3) / 4, 128, 0, st>>>(b, sc.nterms, cut_eff, sc.terms);
+        k_terms<<<(n + 3) / 4, 128, 0, st>>>(b, sc, hq_max_nnz, (uint32_t)HQ_LOG2_SLOTS, hq_tries);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ix->ev[3], st));
         const uint64_t tasks = (uint64_t)n * cut_eff;
         k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);
         CK(cudaGetLastError());
         launches += 2;
-        if (a.first_sorted) {
+        if (ad.first_sorted) {
             k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc);
             CK(cudaGetLastError());
             ++launches;
         }
-        CK(cudaMemsetAsync(ix->d_counters.p, 0, 4, st));
         CK(cudaEventRecord(ix->ev[4], st));
-        a.b = b;
-        a.sc = sc;
-        a.out_scores = d_scores + (uint64_t)q0 * k;
-        a.out_counts = d_counts + q0;
-        k_search<<<ctas, SEARCH_THREADS, smem, st>>>(a);
-        CK(cudaGetLastError());
+        ad.b = ah.b = b;
+        ad.sc = ah.sc = sc;
+        ad.out_scores = ah.out_scores = d_scores + (uint64_t)q0 * k;
+        ad.out_counts = ah.out_counts = d_counts + q0;
+        if (hq_ok) {
+            ah.qlist = sc.qlist_hq;
+            ah.n_list = sc.counters + 4;
+            kh<<<hq_ctas, HQ_THREADS, smem_h, st>>>(ah);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        if (dense_ok) {
+            ad.qlist = sc.qlist_dense;
+            ad.n_list = sc.counters + 5;
+            kd<<<ctas, DENSE_THREADS, smem_d, st>>>(ad);
+            CK(cudaGetLastError());
+            ++launches;
+        }
         CK(cudaEventRecord(ix->ev[5], st));
         const uint64_t tot = (uint64_t)n * k;
         k_finish<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->ix.rec_start, ix->ix.n_docs, sc.out_keys,
-                                                                a.out_counts, k, n, d_ids + (uint64_t)q0 * k);
+                                                                ad.out_counts, k, n, d_ids + (uint64_t)q0 * k);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ix->ev[6], st));
-        launches += 2;
+        ++launches;
         CK(cudaStreamSynchronize(st));
         float ms;
         CK(cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3])); ms_terms += ms;
@@ -440,11 +487,18 @@ int sgpu_index_set_stream(SgpuIndex* ix, void* cuda_stream) {
 int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     if (!ix || !name) return SGPU_EINVAL;
     std::string n(name);
+    if (n == "hq") {
+        ix->hq_enabled = value != 0;
+        return SGPU_OK;
+    }
     if (value <= 0) {
         shost::set_error("option values must be positive");
         return SGPU_EINVAL;
     }
-    if (n == "wave_docs") ix->wave_docs = (uint32_t)value;
+    if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
+    else if (n == "hq_first_wave_docs") ix->hq_first_wave_docs = (uint32_t)value;
+    else if (n == "hq_ctas_per_sm") ix->hq_ctas_per_sm = (int)value;
+    else if (n == "wave_docs") ix->wave_docs = (uint32_t)value;
     else if (n == "first_wave_docs") ix->first_wave_docs = (uint32_t)value;
     else if (n == "ctas") ix->ctas = (int)value;
     else if (n == "scratch_mb") ix->scratch_bytes = (uint64_t)value << 20;

@@ -54,16 +54,32 @@ def test_parity_pruned(oracle_mod, synth_pruned, gpu_pruned, k, cut, hf, srt):
     assert gpu_pruned.last_stats["docs_scored"] >= ref[3]["docs_scored"]
 
 
+@pytest.mark.parametrize("hq", [1, 0])
 @pytest.mark.parametrize("wave,first", [(1, 1), (64, 8), (512, 512), (4096, 4096)])
-def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first):
-    """The speculative wave scheduler is a performance knob only: any wave size replays to the same heap."""
+def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first, hq):
+    """The speculative wave scheduler is a performance knob only: any wave size replays to the same heap,
+    in the hash-query kernel (hq=1) as well as in the dense-query kernel (hq=0)."""
     _, q, index = synth_pruned
     g = GpuIndex(index, 0)
+    g.set_option("hq", hq)
     g.set_option("wave_docs", wave)
     g.set_option("first_wave_docs", first)
+    g.set_option("hq_wave_docs", min(wave, 1024))
+    g.set_option("hq_first_wave_docs", min(first, 1024))
     ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 3, 0.8, first_sorted=True)
     got = g.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8, first_sorted=True)
     assert_same(got, ref, f"wave={wave}")
+
+
+@pytest.mark.parametrize("hq", [1, 0])
+def test_dense_and_hash_kernels_agree(oracle_mod, synth_small, hq):
+    _, q, index = synth_small
+    g = GpuIndex(index, 0)
+    g.set_option("hq", hq)
+    for k, cut, hf, srt in [(10, 3, 0.8, True), (100, 6, 0.9, False)]:
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        assert_same(got, ref, f"hq={hq} k={k}")
 
 
 def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
@@ -71,6 +87,7 @@ def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
     g = GpuIndex(index, 0)
     g.set_option("scratch_mb", 1)
     g.set_option("ctas", 7)
+    g.set_option("hq_ctas_per_sm", 1)
     ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 3, 0.8)
     got = g.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8)
     assert_same(got, ref, "chunked")
