@@ -368,6 +368,7 @@ def main():
             "work": {"docs_scored_gpu": int(stats[-1]["docs_scored"]), "docs_scored_reference": int(ost["docs_scored"]),
                      "blocks_scored_gpu": int(stats[-1]["blocks_scored"]), "blocks_evaluated_reference": int(ost["blocks_evaluated"]),
                      "algorithmic_bytes_per_query": ost["bytes_total"] / nq},
+            "phase_share": (lambda c: [round(x / max(1, sum(c)), 4) for x in c])(stats[-1]["phase_cycles"]),
             "setup_s": timings, "wall_s_timed_region": t_wall, "ms_kernels_per_step": ms_kernels,
         }
         print(json.dumps(out), flush=True)

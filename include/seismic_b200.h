@@ -129,6 +129,8 @@ typedef struct SgpuSearchStats {
     uint64_t blocks_scored;  /* blocks whose docs were read                                     */
     uint64_t blocks_pushed;  /* blocks that survived the exact replay (== reference evaluated)  */
     uint64_t fwd_bytes;      /* bytes of forward-index records read                             */
+    uint64_t phase_cycles[6];/* SM clocks summed over CTAs: fetch+stage, select, gather postings,
+                                score, replay, results (k_search's own phase profile)           */
 } SgpuSearchStats;
 
 typedef struct SgpuIndex SgpuIndex; /* opaque: HBM image + scratch + stream on one device        */

@@ -81,10 +81,12 @@ class SearchStats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_prep", C.c_float), ("ms_summary", C.c_float), ("ms_search", C.c_float),
                 ("ms_finish", C.c_float), ("n_launches", C.c_uint32), ("reserved", C.c_uint32),
                 ("docs_scored", C.c_uint64), ("blocks_scored", C.c_uint64), ("blocks_pushed", C.c_uint64),
-                ("fwd_bytes", C.c_uint64)]
+                ("fwd_bytes", C.c_uint64), ("phase_cycles", C.c_uint64 * 6)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("reserved", "phase_cycles")}
+        d["phase_cycles"] = list(self.phase_cycles)
+        return d
 
 
 class BuildConfig(C.Structure):

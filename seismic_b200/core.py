@@ -219,6 +219,11 @@ class GpuIndex:
         self.dim = host.dim
         self.len = host.len
         self.last_stats: dict = {}
+        # tuning knobs for experiments: SEISMIC_B200_OPTS="hq=2,hq_wave_docs=512" (never changes results)
+        import os
+        for kv in filter(None, os.environ.get("SEISMIC_B200_OPTS", "").split(",")):
+            name, _, val = kv.partition("=")
+            self.set_option(name.strip(), int(val))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
     __syncthreads();
     DenseQuery dq;
     dq.qd = qd;
-    uint32_t heap_n = 0, wkey = 0, widx = 0;
-    float theta = 0.f;
+    SmemHeap heap;
+    heap.reset(a.k, heap_s, heap_k);
     const uint64_t d_lo = (uint64_t)seg * a.seg_docs;
     const uint64_t d_hi = d_lo + a.seg_docs < a.n_docs ? d_lo + a.seg_docs : a.n_docs;
     constexpr uint32_t PER_ROUND = EXACT_THREADS / 8;  // documents per round
@@ -76,17 +76,16 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
                 for (uint32_t i0 = 0; i0 < nc; i0 += 32) {
                     const uint32_t i = i0 + lane;
                     const bool have = i < nc;
-                    heap_offer(have, have ? cand_s[i] : 0.f, have ? cand_k[i] : 0u, heap_s, heap_k, a.k, lane, heap_n,
-                               theta, wkey, widx);
+                    heap.offer(have, have ? cand_s[i] : 0.f, have ? cand_k[i] : 0u, lane);
                 }
-                if (lane == 0) s_ncand = 0, s_full = heap_n == a.k, s_theta = theta, s_wkey = wkey;
+                if (lane == 0) s_ncand = 0, s_full = heap.full(), s_theta = heap.theta, s_wkey = heap.wkey;
             }
             __syncthreads();
         }
     }
     if (warp == 0) {
         const uint64_t o = ((uint64_t)qi * a.n_seg + seg) * a.k;
-        heap_write_sorted(heap_s, heap_k, heap_n, a.k, lane, a.part_keys + o, a.part_scores + o);
+        heap.write_sorted(lane, a.part_keys + o, a.part_scores + o);
     }
 }
 
@@ -97,24 +96,24 @@ __global__ void __launch_bounds__(32) k_exact_merge(const ExactArgs a, const voi
     float* heap_s = reinterpret_cast<float*>(smem_raw);
     uint32_t* heap_k = reinterpret_cast<uint32_t*>(smem_raw + ((a.k + 3) & ~3u) * 4);
     const uint32_t qi = blockIdx.x, lane = threadIdx.x;
-    uint32_t heap_n = 0, wkey = 0, widx = 0;
-    float theta = 0.f;
+    SmemHeap heap;
+    heap.reset(a.k, heap_s, heap_k);
     const uint64_t o = (uint64_t)qi * a.n_seg * a.k;
     const uint32_t total = a.n_seg * a.k;
     for (uint32_t i0 = 0; i0 < total; i0 += 32) {
         const uint32_t i = i0 + lane;
         const uint32_t key = i < total ? a.part_keys[o + i] : 0xffffffffu;
         const bool have = key != 0xffffffffu;
-        heap_offer(have, have ? a.part_scores[o + i] : 0.f, key, heap_s, heap_k, a.k, lane, heap_n, theta, wkey, widx);
+        heap.offer(have, have ? a.part_scores[o + i] : 0.f, key, lane);
     }
     __syncwarp();
     // sorted output: reuse the partial buffers of segment 0 as scratch for keys
     uint32_t* skeys = a.part_keys + o;
-    heap_write_sorted(heap_s, heap_k, heap_n, a.k, lane, skeys, out_scores + (uint64_t)qi * a.k);
+    heap.write_sorted(lane, skeys, out_scores + (uint64_t)qi * a.k);
     __syncwarp();
     for (uint32_t i = lane; i < a.k; i += 32) {
         uint64_t id = ~0ull;
-        if (i < heap_n) {
+        if (i < heap.n) {
             const uint32_t key = skeys[i];
             uint64_t lo = 0, hi = a.n_docs + 1;
             while (lo < hi) {
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(32) k_exact_merge(const ExactArgs a, const voi
         }
         out_ids[(uint64_t)qi * a.k + i] = id;
     }
-    if (lane == 0) out_counts[qi] = heap_n;
+    if (lane == 0) out_counts[qi] = heap.n;
 }
 
 }  // namespace sgpu

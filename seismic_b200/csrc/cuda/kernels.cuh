@@ -81,7 +81,7 @@ struct Scratch {
     uint32_t* qlist_hq;  // [nq] chunk-relative ids of the queries taken by the hash-query kernel
     uint32_t* qlist_dense;
     uint32_t* out_keys;  // [nq_chunk * k]
-    unsigned long long* stats;  // [4] docs_scored, blocks_scored, blocks_pushed, fwd_units
+    unsigned long long* stats;  // [0..3] docs_scored, blocks_scored, blocks_pushed, fwd_units; [4..9] phase clocks
     uint32_t est_stride;
     uint32_t cut_eff;
 };
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(128) k_terms(Batch b, Scratch sc, uint32_t hq_
     // ---- routing + perfect-hash multiplier
     uint32_t mult = 0;
     if (hq_max_nnz > 0 && n <= hq_max_nnz) {
-        if (nt == 0) {
-            mult = 0x9E3779B1u;  // nothing will be staged
+        if (nt == 0 || hq_tries == 0) {
+            mult = 0x9E3779B1u;  // nothing will be staged / byte-indexed query: no hashing needed
         } else {
             const uint32_t words = (1u << hq_log2_slots) >> 5;
             for (uint32_t attempt = 0; attempt < hq_tries && mult == 0; ++attempt) {

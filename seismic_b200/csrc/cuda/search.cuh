@@ -2,13 +2,16 @@
 // scoring and the bounded top-k (reference src/posting_list.rs:115-215, src/utils.rs:12-66,
 // src/inverted_index.rs:180-234).  Persistent kernel; CTAs fetch query ids from an atomic counter.
 //
-// Two instantiations share all the code below:
-//   k_search<128, HashQuery>   "hq": the query lives in a 4096-slot perfect-hash table in shared memory
-//                              (u16/u32 tag + f32 value, collision-free multiplier found by k_terms), ~32 KB per
-//                              CTA, so 7 CTAs = 7 independent queries are resident per SM and hide each other's
-//                              dependent-load and replay latencies.  Used for queries with <= 128 components.
-//   k_search<1024, DenseQuery> the dense f32 query vector (dim x 4 B) in shared memory, one CTA per SM.  Handles
-//                              any query; used for the (rare) queries the hash path cannot take.
+// The kernel is a template over the shared-memory representation of the query:
+//   RankQuery   bitmap over the vocabulary + per-word rank + value array (dim/8 + dim/32 + 1 KB = 5.8 KB at
+//               dim 30522): a forward-index component first tests one bit (96 % of the components of a document
+//               are not in the query and stop there); hits fetch their value through popcount ranking.  Small
+//               enough that a dozen CTAs (= independent queries) are resident per SM and hide each other's
+//               dependent-load latencies, and it needs the fewest shared-memory wavefronts per component.
+//   ByteQuery   byte index per vocabulary entry + value array (dim + 1 KB)
+//   HashQuery   4096-slot perfect hash (tag + value, 24 KB), multiplier found by k_terms
+//   DenseQuery  dense f32 vector (dim x 4 B), one 1024-thread CTA per SM; handles ANY query and is the
+//               fallback for queries with more than 255 distinct components.
 //
 // Exactness.  The reference walks blocks sequentially and skips block b iff the heap is full and
 // est[b] < heap_factor * theta, theta = current k-th best score (src/posting_list.rs:130-132).  theta never
@@ -19,20 +22,28 @@
 // and therefore every later decision — is bit-identical to the sequential algorithm.  The `visited` set of
 // the reference only prevents re-scoring; for results it is equivalent to "never push a doc that is
 // already in the heap" (a doc seen earlier is either still in the heap or has score <= theta and cannot
-// re-enter, KHeap::push is strict — src/utils.rs:36-39), which is what heap_offer checks.
+// re-enter, KHeap::push is strict — src/utils.rs:36-39), which is what the heaps' offer() checks.
+//
+// Arithmetic of a document score (pinned by oracle/oracle_search.cpp ORDER_LANES8): 8 lanes per document, lane
+// g accumulates the 32-byte chunks g, g+8, ... in ascending component order with separate f32 mul and add
+// (no FMA), then a butterfly reduction (xor 4, 2, 1).  Components that are not in the query contribute
+// q = +0.0, so skipping them (RankQuery) leaves every partial sum bit-identical.
 #pragma once
 #include "kernels.cuh"
 
 namespace sgpu {
 
 constexpr int HQ_THREADS = 128;
+constexpr int HQ_D = 2;    // documents in flight per 8-lane group
 constexpr int HQ_LOG2_SLOTS = 12;
 constexpr int HQ_SLOTS = 1 << HQ_LOG2_SLOTS;
-constexpr int HQ_MAX_NNZ = 128;  // queries with more components take the dense kernel
+constexpr int HQ_MAX_NNZ = 128;  // HashQuery: queries with more components take the dense kernel
 constexpr int HQ_TRIES = 64;
 constexpr int DENSE_THREADS = 1024;
+#ifndef SGPU_LD256
+#define SGPU_LD256 0
+#endif
 
-__device__ __forceinline__ uint32_t hq_mult(uint32_t attempt) { return (2u * attempt + 1u) * 0x9E3779B1u; }
 __device__ __forceinline__ uint32_t hq_slot(uint32_t c, uint32_t mult) { return (c * mult) >> (32 - HQ_LOG2_SLOTS); }
 
 struct SearchArgs {
@@ -47,10 +58,8 @@ struct SearchArgs {
     int first_sorted;
     uint32_t wave_docs;        // soft cap of documents per wave
     uint32_t first_wave_docs;  // soft cap for the first wave of a query (heap still empty)
-    uint32_t buf_docs;         // capacity of the wave buffers (>= largest block, >= wave caps)
-    uint32_t qd_words;         // dense kernel: floats reserved for the dense query (dim rounded up)
-    uint64_t* g_docs;          // optional global wave buffers (when buf_docs does not fit in smem)
-    float* g_scores;
+    uint32_t buf_docs;         // capacity of the wave buffers (>= wave caps); larger blocks are split
+    uint32_t qd_words;         // 32-bit words of the query table (meaning depends on the query type)
     float* out_scores;         // [nq*k] (chunk-relative)
     uint32_t* out_counts;      // [nq]
 };
@@ -62,19 +71,39 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
                  : "l"(p));
     return r;
 }
+// one whole 32-byte chunk (8 components + 8 values): a single 256-bit load (LDG.E.256, sm_100) or two 128-bit loads
+__device__ __forceinline__ void ld_chunk(const uint4* p, uint4& c, uint4& v) {
+#if SGPU_LD256
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+#else
+    c = ld_stream(p);
+    v = ld_stream(p + 1);
+#endif
+}
+
+__device__ __forceinline__ float h_lo(uint32_t vw) { return __low2float(*reinterpret_cast<const __half2*>(&vw)); }
+__device__ __forceinline__ float h_hi(uint32_t vw) { return __high2float(*reinterpret_cast<const __half2*>(&vw)); }
 
 // ---- query representations in shared memory -------------------------------------------------------------
+// Interface: bytes(a) shared memory, init (once per CTA), stage/unstage (per query),
+// mac2(acc, cw, vw): acc += q[c_lo]*v_lo ; acc += q[c_hi]*v_hi for the two (u16 component, f16 value) pairs
+// packed in cw / vw, in that order, mul then add.
 struct DenseQuery {
     float* qd;
-    __device__ __forceinline__ float operator()(uint32_t c) const { return qd[c]; }
     static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return (size_t)a.qd_words * 4; }
+    __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
+        acc = __fadd_rn(acc, __fmul_rn(qd[cw & 0xffffu], h_lo(vw)));
+        return __fadd_rn(acc, __fmul_rn(qd[cw >> 16], h_hi(vw)));
+    }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
         qd = reinterpret_cast<float*>(base);
         for (uint32_t i = tid; i < a.qd_words; i += T) qd[i] = 0.f;
     }
     template <int T>
-    __device__ __forceinline__ void stage(const Batch& b, const Scratch&, uint32_t q, uint64_t qo, uint32_t qn,
+    __device__ __forceinline__ void stage(const Batch& b, const Scratch&, uint32_t, uint64_t qo, uint32_t qn,
                                           uint32_t tid) {
         for (uint32_t i = tid; i < qn; i += T) {
             const uint32_t c = b.q_comps[qo + i];
@@ -87,16 +116,53 @@ struct DenseQuery {
     }
 };
 
+struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); vals[0] = +0.0
+    uint8_t* qidx;
+    float* vals;
+    static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return 1024 + (size_t)a.qd_words * 4; }
+    __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
+        acc = __fadd_rn(acc, __fmul_rn(vals[qidx[cw & 0xffffu]], h_lo(vw)));
+        return __fadd_rn(acc, __fmul_rn(vals[qidx[cw >> 16]], h_hi(vw)));
+    }
+    template <int T>
+    __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
+        vals = reinterpret_cast<float*>(base);
+        qidx = base + 1024;
+        for (uint32_t i = tid; i < 256; i += T) vals[i] = 0.f;
+        uint32_t* w = reinterpret_cast<uint32_t*>(qidx);
+        for (uint32_t i = tid; i < a.qd_words; i += T) w[i] = 0u;
+    }
+    template <int T>
+    __device__ __forceinline__ void stage(const Batch& b, const Scratch&, uint32_t, uint64_t qo, uint32_t qn,
+                                          uint32_t tid) {
+        for (uint32_t i = tid; i < qn; i += T) {
+            const uint32_t c = b.q_comps[qo + i];
+            if (i + 1 == qn || b.q_comps[qo + i + 1] != c) {  // last duplicate wins
+                qidx[c] = (uint8_t)(i + 1);
+                vals[i + 1] = b.q_vals[qo + i];
+            }
+        }
+    }
+    template <int T>
+    __device__ __forceinline__ void unstage(const Batch& b, uint64_t qo, uint32_t qn, uint32_t tid) {
+        for (uint32_t i = tid; i < qn; i += T) qidx[b.q_comps[qo + i]] = 0;
+    }
+};
+
 struct HashQuery {
     uint16_t* tags;
     float* vals;
     uint32_t mult;
-    __device__ __forceinline__ float operator()(uint32_t c) const {
+    static __device__ __forceinline__ size_t bytes(const SearchArgs&) { return (size_t)HQ_SLOTS * 6; }
+    __device__ __forceinline__ float get(uint32_t c) const {
         const uint32_t s = hq_slot(c, mult);
         const float v = vals[s];
         return tags[s] == (uint16_t)c ? v : 0.f;
     }
-    static __device__ __forceinline__ size_t bytes(const SearchArgs&) { return (size_t)HQ_SLOTS * 6; }
+    __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
+        acc = __fadd_rn(acc, __fmul_rn(get(cw & 0xffffu), h_lo(vw)));
+        return __fadd_rn(acc, __fmul_rn(get(cw >> 16), h_hi(vw)));
+    }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs&, uint32_t tid) {
         vals = reinterpret_cast<float*>(base);
@@ -127,44 +193,78 @@ struct HashQuery {
     }
 };
 
-// acc += q[c] * v for the 8 (component, value) pairs of one chunk, ascending, mul then add (no FMA).
+// bm: one bit per vocabulary entry; pre[w]: rank (among the query's distinct components) of the first component
+// of bitmap word w, valid for words that have a bit set; vals[rank].  <= 255 distinct components.
+struct RankQuery {
+    uint32_t* bm;
+    uint8_t* pre;
+    float* vals;
+    // qd_words = number of bitmap words (dim/32 rounded up to a multiple of 4)
+    static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return 1024 + (size_t)a.qd_words * 5; }
+    __device__ __forceinline__ float mac(float acc, uint32_t c, uint32_t vw, bool hi) const {
+        const uint32_t w = bm[c >> 5];
+        if ((w >> (c & 31)) & 1u) {  // ~4 % of a document's components
+            const uint32_t r = pre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
+            acc = __fadd_rn(acc, __fmul_rn(vals[r], hi ? h_hi(vw) : h_lo(vw)));
+        }
+        return acc;
+    }
+    __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
+        acc = mac(acc, cw & 0xffffu, vw, false);
+        return mac(acc, cw >> 16, vw, true);
+    }
+    template <int T>
+    __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
+        vals = reinterpret_cast<float*>(base);
+        bm = reinterpret_cast<uint32_t*>(base + 1024);
+        pre = base + 1024 + (size_t)a.qd_words * 4;
+        for (uint32_t i = tid; i < a.qd_words; i += T) bm[i] = 0u;
+    }
+    template <int T>
+    __device__ __forceinline__ void stage(const Batch& b, const Scratch&, uint32_t, uint64_t qo, uint32_t qn,
+                                          uint32_t tid) {
+        const uint32_t* qc = b.q_comps + qo;
+        for (uint32_t i = tid; i < qn; i += T) {
+            const uint32_t c = qc[i];
+            if (i + 1 == qn || qc[i + 1] != c) {  // last occurrence of c carries the value (last duplicate wins)
+                uint32_t rank = 0, first_in_word = 1;
+                for (uint32_t j = 0; j < i; ++j) {
+                    const bool run_end = qc[j] != qc[j + 1];
+                    rank += run_end;
+                    if (run_end && (qc[j] >> 5) == (c >> 5)) first_in_word = 0;
+                }
+                atomicOr(&bm[c >> 5], 1u << (c & 31));
+                vals[rank] = b.q_vals[qo + i];
+                if (first_in_word) pre[c >> 5] = (uint8_t)rank;
+            }
+        }
+    }
+    template <int T>
+    __device__ __forceinline__ void unstage(const Batch& b, uint64_t qo, uint32_t qn, uint32_t tid) {
+        for (uint32_t i = tid; i < qn; i += T) bm[b.q_comps[qo + i] >> 5] = 0u;
+    }
+};
+
+// acc += q[c] * v for the 8 (component, value) pairs of one chunk, ascending
 template <class Q>
 __device__ __forceinline__ float chunk_dot(float acc, const uint4 c, const uint4 v, const Q& q) {
-    const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
-    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vw[j]));
-        acc = __fadd_rn(acc, __fmul_rn(q(cw[j] & 0xffffu), f.x));
-        acc = __fadd_rn(acc, __fmul_rn(q(cw[j] >> 16), f.y));
-    }
-    return acc;
+    acc = q.mac2(acc, c.x, v.x);
+    acc = q.mac2(acc, c.y, v.y);
+    acc = q.mac2(acc, c.z, v.z);
+    return q.mac2(acc, c.w, v.w);
 }
 
 // Score one document record (nch 32-byte chunks at `rec`) with an 8-lane group; lane8 handles chunks
-// lane8, lane8+8, ...  The caller reduces the 8 partial sums with xor-shuffles 4, 2, 1.
+// lane8, lane8+8, ...  The caller reduces the 8 partial sums with group_reduce.
 template <class Q>
 __device__ __forceinline__ float score_rec(const uint4* __restrict__ rec, uint32_t nch, uint32_t lane8, const Q& q) {
     float acc = 0.f;
-    uint32_t m = lane8;
-    // two chunks in flight per lane per trip (covers documents up to 128 components in one trip)
-    for (; m + 8 < nch; m += 16) {
-        const uint4 c0 = ld_stream(rec + 2 * m), v0 = ld_stream(rec + 2 * m + 1);
-        const uint4 c1 = ld_stream(rec + 2 * (m + 8)), v1 = ld_stream(rec + 2 * (m + 8) + 1);
-        acc = chunk_dot(acc, c0, v0, q);
-        acc = chunk_dot(acc, c1, v1, q);
-    }
-    if (m < nch) {
-        const uint4 c0 = ld_stream(rec + 2 * m), v0 = ld_stream(rec + 2 * m + 1);
-        acc = chunk_dot(acc, c0, v0, q);
+    for (uint32_t m = lane8; m < nch; m += 8) {
+        uint4 c, v;
+        ld_chunk(rec + 2 * m, c, v);
+        acc = chunk_dot(acc, c, v, q);
     }
     return acc;
-}
-template <class Q>
-__device__ __forceinline__ float score_doc(const uint4* __restrict__ fwd, uint64_t posting, uint32_t lane8,
-                                           const Q& q) {
-    const uint32_t nnz = (uint32_t)(posting & 0xffffu);
-    return score_rec(fwd + (posting >> 16) * 2, (nnz + 7) >> 3, lane8, q);
 }
 __device__ __forceinline__ float group_reduce(float s) {
     s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 4));
@@ -172,104 +272,225 @@ __device__ __forceinline__ float group_reduce(float s) {
     return __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));
 }
 
-// ---- bounded top-k kept by ONE warp in shared memory -------------------------------------------------------
+// Score D documents with one 8-lane group, round by round: in round r lane8 handles chunk lane8 + 8r of every
+// document; all loads of a round are issued before the first use.  `rounds` must be warp-uniform.
+template <int D, class Q>
+__device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const uint64_t (&post)[D], uint32_t lane8,
+                                           uint32_t rounds, const Q& q, float (&acc)[D]) {
+    const uint4* rec[D];
+    uint32_t nch[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        rec[j] = fwd + (post[j] >> 16) * 2 + 2 * lane8;
+        nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
+        acc[j] = 0.f;
+    }
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t m = lane8 + 8 * r;
+        uint4 c[D], v[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            if (m < nch[j]) ld_chunk(rec[j] + 16 * r, c[j], v[j]);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            if (m < nch[j]) acc[j] = chunk_dot(acc[j], c[j], v[j], q);
+    }
+}
+
+// ---- bounded top-k kept by ONE warp ------------------------------------------------------------------------
 __device__ __forceinline__ bool better(float s, uint32_t key, float ws, uint32_t wkey) {
     return s > ws || (s == ws && key < wkey);
 }
 
-// recompute the worst retained item (lowest score, ties: largest key)
-__device__ __forceinline__ void find_worst(const float* hs, const uint32_t* hk, uint32_t n, uint32_t lane, float& theta,
-                                           uint32_t& wkey, uint32_t& widx) {
-    float s = 0.f;
-    uint32_t key = 0, idx = 0xffffffffu;
-    for (uint32_t i = lane; i < n; i += 32) {
-        const float si = hs[i];
-        const uint32_t ki = hk[i];
-        if (idx == 0xffffffffu || better(s, key, si, ki)) s = si, key = ki, idx = i;
+// KHeap (src/utils.rs:12-66) for k <= 32: lane i holds the i-th best retained item (sorted, registers only).
+struct RegHeap {
+    float s;        // per lane
+    uint32_t key;   // per lane
+    uint32_t n, k;  // warp-uniform
+    float theta;    // worst retained score (valid when full)
+    uint32_t wkey;
+    __device__ __forceinline__ void reset(uint32_t kk, float*, uint32_t*) {
+        n = 0, k = kk, theta = 0.f, wkey = 0, s = 0.f, key = 0;
     }
-    for (int sh = 16; sh > 0; sh >>= 1) {
-        const float os = __shfl_xor_sync(0xffffffffu, s, sh);
-        const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, sh);
-        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, sh);
-        if (oi != 0xffffffffu && (idx == 0xffffffffu || better(s, key, os, ok))) s = os, key = ok, idx = oi;
+    __device__ __forceinline__ bool full() const { return n == k; }
+    // push up to 32 items, one per lane; items already retained (same key) are ignored
+    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane) {
+        for (;;) {
+            const bool c = have && (n < k || better(sc, ky, theta, wkey));
+            const uint32_t m = __ballot_sync(0xffffffffu, c);
+            if (!m) break;
+            const int src = __ffs(m) - 1;
+            const float bs = __shfl_sync(0xffffffffu, sc, src);
+            const uint32_t bk = __shfl_sync(0xffffffffu, ky, src);
+            if ((int)lane == src) have = false;
+            if (__ballot_sync(0xffffffffu, lane < n && key == bk)) continue;
+            const uint32_t pos = __popc(__ballot_sync(0xffffffffu, lane < n && better(s, key, bs, bk)));
+            const float ps = __shfl_up_sync(0xffffffffu, s, 1);
+            const uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+            const uint32_t last = n < k ? n : k - 1;
+            if (lane > pos && lane <= last) s = ps, key = pk;
+            if (lane == pos) s = bs, key = bk;
+            if (n < k) ++n;
+            if (n == k) {
+                theta = __shfl_sync(0xffffffffu, s, k - 1);
+                wkey = __shfl_sync(0xffffffffu, key, k - 1);
+            }
+        }
     }
-    theta = s;
-    wkey = key;
-    widx = idx;
-}
+    __device__ __forceinline__ void write_sorted(uint32_t lane, uint32_t* out_keys, float* out_scores) const {
+        for (uint32_t i = lane; i < k; i += 32) {
+            const bool ok = i < n;  // only i == lane < 32 can be valid
+            out_keys[i] = ok ? key : 0xffffffffu;
+            out_scores[i] = ok ? s : -INFINITY;
+        }
+    }
+};
 
-// Warp-cooperative KHeap::push (src/utils.rs:32-41) of up to 32 items, one per lane (`have`).  Items that are
-// already retained (same key) are ignored — the `visited` equivalence explained at the top.  The retained
-// set after the call does not depend on the order in which lanes are served (total order on (score, key)).
-__device__ __forceinline__ void heap_offer(bool have, const float sc, const uint32_t key, float* hs, uint32_t* hk,
-                                           const uint32_t k, const uint32_t lane, uint32_t& heap_n, float& theta,
-                                           uint32_t& wkey, uint32_t& widx) {
-    for (;;) {
-        const bool fl = heap_n == k;
-        const bool c = have && (!fl || better(sc, key, theta, wkey));
-        const uint32_t m = __ballot_sync(0xffffffffu, c);
-        if (!m) break;
-        const int src = __ffs(m) - 1;
-        const float bs = __shfl_sync(0xffffffffu, sc, src);
-        const uint32_t bk = __shfl_sync(0xffffffffu, key, src);
-        if ((int)lane == src) have = false;
-        bool dup = false;
-        for (uint32_t hh = lane; hh < heap_n; hh += 32) dup |= hk[hh] == bk;
-        if (__any_sync(0xffffffffu, dup)) continue;
-        const uint32_t slot = fl ? widx : heap_n;
-        if (lane == 0) hs[slot] = bs, hk[slot] = bk;
-        if (!fl) ++heap_n;
-        __syncwarp();
-        if (heap_n == k) find_worst(hs, hk, heap_n, lane, theta, wkey, widx);
+// KHeap for any k (<= 1024): unsorted arrays in shared memory + tracked worst item.
+struct SmemHeap {
+    float* hs;
+    uint32_t* hk;
+    uint32_t n, k, wkey, widx;
+    float theta;
+    __device__ __forceinline__ void reset(uint32_t kk, float* s, uint32_t* ky) {
+        hs = s, hk = ky, n = 0, k = kk, theta = 0.f, wkey = 0, widx = 0;
     }
-}
-
-// warp-cooperative: write the retained items best first (rank sort) and pad to k
-__device__ __forceinline__ void heap_write_sorted(const float* hs, const uint32_t* hk, uint32_t heap_n, uint32_t k,
-                                                  uint32_t lane, uint32_t* out_keys, float* out_scores) {
-    for (uint32_t i = lane; i < heap_n; i += 32) {
-        const float si = hs[i];
-        const uint32_t ki = hk[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < heap_n; ++j) rank += better(hs[j], hk[j], si, ki);
-        out_keys[rank] = ki;
-        out_scores[rank] = si;
+    __device__ __forceinline__ bool full() const { return n == k; }
+    __device__ __forceinline__ void find_worst(uint32_t lane) {
+        float s = 0.f;
+        uint32_t key = 0, idx = 0xffffffffu;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const float si = hs[i];
+            const uint32_t ki = hk[i];
+            if (idx == 0xffffffffu || better(s, key, si, ki)) s = si, key = ki, idx = i;
+        }
+        for (int sh = 16; sh > 0; sh >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, s, sh);
+            const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, sh);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, sh);
+            if (oi != 0xffffffffu && (idx == 0xffffffffu || better(s, key, os, ok))) s = os, key = ok, idx = oi;
+        }
+        theta = s, wkey = key, widx = idx;
     }
-    for (uint32_t i = heap_n + lane; i < k; i += 32) out_keys[i] = 0xffffffffu, out_scores[i] = -INFINITY;
-}
+    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane) {
+        for (;;) {
+            const bool fl = n == k;
+            const bool c = have && (!fl || better(sc, ky, theta, wkey));
+            const uint32_t m = __ballot_sync(0xffffffffu, c);
+            if (!m) break;
+            const int src = __ffs(m) - 1;
+            const float bs = __shfl_sync(0xffffffffu, sc, src);
+            const uint32_t bk = __shfl_sync(0xffffffffu, ky, src);
+            if ((int)lane == src) have = false;
+            bool dup = false;
+            for (uint32_t hh = lane; hh < n; hh += 32) dup |= hk[hh] == bk;
+            if (__any_sync(0xffffffffu, dup)) continue;
+            const uint32_t slot = fl ? widx : n;
+            if (lane == 0) hs[slot] = bs, hk[slot] = bk;
+            if (!fl) ++n;
+            __syncwarp();
+            if (n == k) find_worst(lane);
+        }
+    }
+    __device__ __forceinline__ void write_sorted(uint32_t lane, uint32_t* out_keys, float* out_scores) const {
+        for (uint32_t i = lane; i < n; i += 32) {
+            const float si = hs[i];
+            const uint32_t ki = hk[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; ++j) rank += better(hs[j], hk[j], si, ki);
+            out_keys[rank] = ki;
+            out_scores[rank] = si;
+        }
+        for (uint32_t i = n + lane; i < k; i += 32) out_keys[i] = 0xffffffffu, out_scores[i] = -INFINITY;
+    }
+};
 
 // -----------------------------------------------------------------------------------------------------------
-template <int T, class Q>
-__global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 7)) k_search(const SearchArgs a) {
+// T threads per CTA, OCC = CTAs per SM the register allocation is budgeted for, D = documents per 8-lane group
+// per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise).
+template <int T, int OCC, int D, class Q, class H>
+__global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     constexpr int NW = T / 32;      // warps
-    constexpr int GROUPS = T / 8;   // 8-lane groups, one document each
+    constexpr int GROUPS = T / 8;   // 8-lane groups
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Q query;
     query.template init<T>(smem_raw, a, threadIdx.x);
-    unsigned char* p = smem_raw + Q::bytes(a);
-    uint32_t* cand_blk = reinterpret_cast<uint32_t*>(p);  p += T * 4;
+    unsigned char* p = smem_raw + ((Q::bytes(a) + 15) & ~(size_t)15);
     uint32_t* cand_end = reinterpret_cast<uint32_t*>(p);  p += T * 4;
     float* cand_est = reinterpret_cast<float*>(p);        p += T * 4;
+    uint32_t* cand_p0 = reinterpret_cast<uint32_t*>(p);   p += T * 4;
     float* heap_s = reinterpret_cast<float*>(p);          p += ((a.k + 3) & ~3u) * 4;
     uint32_t* heap_k = reinterpret_cast<uint32_t*>(p);    p += ((a.k + 3) & ~3u) * 4;
-    uint64_t* docs = a.g_docs ? a.g_docs + (size_t)blockIdx.x * a.buf_docs : reinterpret_cast<uint64_t*>(p);
-    if (!a.g_docs) p += (size_t)a.buf_docs * 8;
-    float* scores = a.g_scores ? a.g_scores + (size_t)blockIdx.x * a.buf_docs : reinterpret_cast<float*>(p);
+    uint64_t* docs = reinterpret_cast<uint64_t*>(p);      p += (size_t)a.buf_docs * 8;
+    float* scores = reinterpret_cast<float*>(p);          p += (size_t)a.buf_docs * 4;
+    uint32_t* surv = reinterpret_cast<uint32_t*>(p);  // bit d: document d of the wave can still enter the heap
 
     __shared__ uint32_t s_q;
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
-    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt;
+    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0;
     __shared__ float s_theta;
-    __shared__ uint32_t s_full;
+    __shared__ uint32_t s_full, s_wkey;
+    // phase clocks (thread 0 only, kept in shared memory to spare registers):
+    // 0 fetch+stage, 1 select, 2 gather postings, 3 score, 4 replay, 5 results, [6] = last mark
+    __shared__ long long s_ph[7];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lane8 = tid & 7;
+    const uint32_t lane8 = tid & 7, grp = tid >> 3;
     const uint32_t k = a.k;
 
-    // warp-0 private heap state (registers, warp-uniform)
-    uint32_t heap_n = 0, wkey = 0, widx = 0;
-    float theta = 0.f;
-    unsigned long long st_docs = 0, st_blocks = 0, st_pushed = 0, st_units = 0;
+    H heap;  // live in warp 0 only
+    heap.reset(k, heap_s, heap_k);
+    uint32_t st_docs = 0, st_blocks = 0, st_pushed = 0, st_units = 0;  // per-CTA totals fit 32 bits
+    if (tid == 0) {
+        for (int i = 0; i < 6; ++i) s_ph[i] = 0;
+        s_ph[6] = clock64();
+    }
+    auto lap = [&](int i) {
+        if (tid == 0) {
+            const long long now = clock64();
+            s_ph[i] += now - s_ph[6];
+            s_ph[6] = now;
+        }
+    };
+
+    // score docs[0, n) of the wave buffer into scores[] and mark the documents that can still enter the heap
+    auto score_wave = [&](uint32_t n) {
+        const bool w_full = s_full != 0;
+        const float w_theta = s_theta;
+        const uint32_t w_wkey = s_wkey;
+        for (uint32_t dbase = 0; dbase < n; dbase += D * GROUPS) {  // CTA-uniform trip count
+            uint64_t post[D];
+            uint32_t mx = 0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const uint32_t d = dbase + j * GROUPS + grp;
+                post[j] = d < n ? docs[d] : 0ull;  // nnz 0 -> no loads, score unused
+                mx = max(mx, (uint32_t)(post[j] & 0xffffu));
+            }
+            const uint32_t rounds = (__reduce_max_sync(0xffffffffu, mx) + 63) >> 6;
+            float acc[D];
+            score_docs<D>(a.ix.fwd, post, lane8, rounds, query, acc);
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float s = group_reduce(acc[j]);
+                const uint32_t d = dbase + j * GROUPS + grp;
+                if (lane8 == 0 && d < n) {
+                    scores[d] = s;
+                    // theta only grows: a document that cannot enter the heap as of the wave start never will
+                    if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey))
+                        atomicOr(&surv[d >> 5], 1u << (d & 31));
+                }
+            }
+        }
+    };
+    // warp 0: offer the surviving documents of wave slots [c0, c1) to the heap
+    auto push_range = [&](uint32_t c0, uint32_t c1) {
+        for (uint32_t base = c0 & ~31u; base < c1; base += 32) {
+            const uint32_t i = base + lane;
+            const bool have = i >= c0 && i < c1 && ((surv[base >> 5] >> lane) & 1u);
+            heap.offer(have, have ? scores[i] : 0.f, have ? (uint32_t)(docs[i] >> 16) : 0u, lane);
+        }
+    };
 
     for (;;) {
         __syncthreads();
@@ -281,9 +502,10 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 7)) k_search(const SearchA
         const uint32_t qn = (uint32_t)(a.b.q_off[a.b.q_base + q + 1] - qo);
         const uint32_t nt = a.sc.nterms[q];  // 0 for invalid queries
         if (nt > 0) query.template stage<T>(a.b, a.sc, q, qo, qn, tid);
-        heap_n = 0;
-        if (tid == 0) s_full = 0, s_theta = 0.f;
+        heap.reset(k, heap_s, heap_k);
+        if (tid == 0) s_full = 0, s_theta = 0.f, s_wkey = 0;
         __syncthreads();
+        lap(0);
 
         bool first_wave = true;
         for (uint32_t t = 0; t < nt; ++t) {
@@ -302,10 +524,10 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 7)) k_search(const SearchA
                 const uint32_t cap = first_wave ? a.first_wave_docs : a.wave_docs;
                 const uint32_t pos = pos0 + tid;
                 bool pass = false;
-                uint32_t blk = 0, nd = 0, p0 = 0;
+                uint32_t nd = 0, p0 = 0;
                 float e = 0.f;
                 if (pos < B) {
-                    blk = ord ? (uint32_t)ord[pos] : pos;
+                    const uint32_t blk = ord ? (uint32_t)ord[pos] : pos;
                     e = est[blk];
                     pass = !full || !(e < thr);
                     if (pass) {
@@ -324,7 +546,7 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 7)) k_search(const SearchA
                 if (lane == 31) s_warp_docs[warp] = cd, s_warp_cnt[warp] = cc;
                 if (tid == 0) s_first_rej = 0xffffffffu;
                 __syncthreads();
-                if (tid == 0) s_wave_docs = 0, s_wave_cnt = 0;  // every thread has consumed the previous wave's totals
+                if (tid == 0) s_wave_docs = 0, s_wave_cnt = 0, s_big_nd = 0;  // previous wave's totals are consumed
                 if (warp == 0) {
                     uint32_t wd = lane < NW ? s_warp_docs[lane] : 0u, wc = lane < NW ? s_warp_cnt[lane] : 0u;
 #pragma unroll
@@ -337,83 +559,128 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 7)) k_search(const SearchA
                 }
                 __syncthreads();
                 if (warp > 0) cd += s_warp_docs[warp - 1], cc += s_warp_cnt[warp - 1];
-                // accept while the wave stays within its soft cap; the first passing block is always accepted
-                // (buf_docs >= largest block); nothing may exceed the buffer capacity
-                const bool accepted = pass && (cc == 1 || cd <= cap) && cd <= a.buf_docs;
+                // accept while the wave stays within its soft cap; the first passing block is accepted whenever it
+                // fits the buffer; a first passing block larger than the buffer is processed alone, in parts
+                const bool accepted = pass && cd <= (cc == 1 ? a.buf_docs : cap);
                 if (pass && !accepted) atomicMin(&s_first_rej, pos);
+                if (pass && cc == 1 && !accepted) s_big_nd = nd, s_big_p0 = p0;
                 __syncthreads();
                 const uint32_t first_rej = s_first_rej;
                 const bool in_wave = pass && pos < first_rej;
                 if (in_wave) {
-                    cand_blk[cc - 1] = blk;
                     cand_end[cc - 1] = cd;
                     cand_est[cc - 1] = e;
-                    // ---------------- phase 2: copy the block's postings into the wave buffer
-                    const uint32_t s0 = cd - nd;
-                    for (uint32_t i = 0; i < nd; ++i) docs[s0 + i] = posts[p0 + i];
+                    cand_p0[cc - 1] = p0;
                     atomicMax(&s_wave_docs, cd);
                     atomicMax(&s_wave_cnt, cc);
                 }
                 __syncthreads();
-                const uint32_t n_docs = s_wave_docs, n_cand = s_wave_cnt;
+                const uint32_t n_docs = s_wave_docs, n_cand = s_wave_cnt, big_nd = s_big_nd, big_p0 = s_big_p0;
+                lap(1);
+                if (n_cand == 0 && big_nd) {
+                    // ---------------- oversized block: it passed the test against the live theta (no other block is
+                    // in flight), so the reference evaluates it; score and push it part by part
+                    for (uint32_t off = 0; off < big_nd; off += a.buf_docs) {
+                        const uint32_t part = min(a.buf_docs, big_nd - off);
+                        for (uint32_t i = tid; i < part; i += T) docs[i] = posts[big_p0 + off + i];
+                        for (uint32_t i = tid; i < (part + 31) >> 5; i += T) surv[i] = 0u;
+                        __syncthreads();
+                        score_wave(part);
+                        __syncthreads();
+                        if (warp == 0) {
+                            st_docs += part;
+                            for (uint32_t i = lane; i < part; i += 32) st_units += ((uint32_t)(docs[i] & 0xffffu) + 7) >> 3;
+                            push_range(0, part);
+                            if (lane == 0) s_full = heap.full(), s_theta = heap.theta, s_wkey = heap.wkey;
+                        }
+                        __syncthreads();
+                    }
+                    if (warp == 0) ++st_blocks, ++st_pushed;
+                    first_wave = false;
+                    pos0 = first_rej + 1;
+                    lap(3);
+                    continue;
+                }
                 pos0 = first_rej != 0xffffffffu ? first_rej : pos0 + T;
                 if (n_cand == 0) continue;
                 first_wave = false;
-                // ---------------- phase 3: score, one document per 8-lane group, two documents in flight
-                for (uint32_t dbase = warp * 4; dbase < n_docs; dbase += 2 * GROUPS) {  // warp-uniform trip count
-                    const uint32_t d = dbase + (lane >> 3), d1 = d + GROUPS;
-                    const uint64_t pa = d < n_docs ? docs[d] : 0ull;  // nnz 0 -> no loads, score unused
-                    const uint64_t pb = d1 < n_docs ? docs[d1] : 0ull;
-                    float sa = score_doc(a.ix.fwd, pa, lane8, query);
-                    float sb = score_doc(a.ix.fwd, pb, lane8, query);
-                    sa = group_reduce(sa);
-                    sb = group_reduce(sb);
-                    if (lane8 == 0) {
-                        if (d < n_docs) scores[d] = sa;
-                        if (d1 < n_docs) scores[d1] = sb;
+                // ---------------- phase 2: gather the postings of all candidate blocks into the wave buffer
+                // (flat over document slots; the owning block is found by binary search over cand_end)
+                for (uint32_t i = tid; i < (n_docs + 31) >> 5; i += T) surv[i] = 0u;
+                for (uint32_t i = tid; i < n_docs; i += T) {
+                    uint32_t lo = 0, hi = n_cand - 1;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (cand_end[mid] <= i) lo = mid + 1;
+                        else hi = mid;
                     }
+                    const uint32_t start = lo ? cand_end[lo - 1] : 0u;
+                    docs[i] = posts[cand_p0[lo] + (i - start)];
                 }
                 __syncthreads();
+                lap(2);
+                // ---------------- phase 3: score the wave
+                score_wave(n_docs);
+                __syncthreads();
+                lap(3);
                 // ---------------- phase 4: exact replay by warp 0
                 if (warp == 0) {
                     st_docs += n_docs;
                     st_blocks += n_cand;
                     for (uint32_t i = lane; i < n_docs; i += 32) st_units += ((uint32_t)(docs[i] & 0xffffu) + 7) >> 3;
-                    for (uint32_t j = 0; j < n_cand; ++j) {
-                        const float ej = cand_est[j];
-                        if (heap_n == k && ej < __fmul_rn(a.heap_factor, theta)) continue;
-                        ++st_pushed;
-                        const uint32_t s0 = j ? cand_end[j - 1] : 0u, s1 = cand_end[j];
-                        for (uint32_t base = s0; base < s1; base += 32) {
-                            const uint32_t i = base + lane;
-                            const bool have = i < s1;
-                            const float sc_i = have ? scores[i] : 0.f;
-                            const uint64_t pi = have ? docs[i] : 0ull;
-                            heap_offer(have, sc_i, (uint32_t)(pi >> 16), heap_s, heap_k, k, lane, heap_n, theta, wkey,
-                                       widx);
+                    // 32 candidate blocks at a time: blocks without survivors only need the skip test (counted,
+                    // heap untouched); the first block WITH survivors that passes the test against the live theta
+                    // is pushed, which may raise theta, so the scan restarts right after it.
+                    uint32_t j0 = 0;
+                    while (j0 < n_cand) {
+                        const uint32_t j = j0 + lane;
+                        const bool valid = j < n_cand;
+                        const uint32_t s0 = valid && j ? cand_end[j - 1] : 0u, s1 = valid ? cand_end[j] : 0u;
+                        bool has = false;
+                        if (valid)
+                            for (uint32_t w = s0 >> 5; w <= (s1 - 1) >> 5; ++w) {
+                                uint32_t bits = surv[w];
+                                if (w == (s0 >> 5)) bits &= 0xffffffffu << (s0 & 31);
+                                if (w == ((s1 - 1) >> 5)) bits &= 0xffffffffu >> (31 - ((s1 - 1) & 31));
+                                has |= bits != 0;
+                            }
+                        const bool passes =
+                            valid && !(heap.full() && cand_est[j] < __fmul_rn(a.heap_factor, heap.theta));
+                        const uint32_t pm = __ballot_sync(0xffffffffu, passes);
+                        const uint32_t hm = __ballot_sync(0xffffffffu, passes && has);
+                        if (!hm) {
+                            st_pushed += __popc(pm);
+                            j0 += 32;
+                            continue;
                         }
+                        const int f = __ffs(hm) - 1;
+                        st_pushed += __popc(pm & ((2u << f) - 1u));
+                        push_range(__shfl_sync(0xffffffffu, s0, f), __shfl_sync(0xffffffffu, s1, f));
+                        j0 += (uint32_t)f + 1;
                     }
-                    if (lane == 0) s_full = heap_n == k, s_theta = theta;
+                    if (lane == 0) s_full = heap.full(), s_theta = heap.theta, s_wkey = heap.wkey;
                 }
                 __syncthreads();
+                lap(4);
             }
         }
-        // ---------------- results: best first (rank sort by warp 0), padded
+        // ---------------- results: best first, padded
         if (warp == 0) {
-            heap_write_sorted(heap_s, heap_k, heap_n, k, lane, a.sc.out_keys + (uint64_t)q * k,
-                              a.out_scores + (uint64_t)q * k);
-            if (lane == 0) a.out_counts[q] = heap_n;
+            heap.write_sorted(lane, a.sc.out_keys + (uint64_t)q * k, a.out_scores + (uint64_t)q * k);
+            if (lane == 0) a.out_counts[q] = heap.n;
         }
         __syncthreads();
         if (nt > 0) query.template unstage<T>(a.b, qo, qn, tid);
+        lap(5);
     }
     if (warp == 0)
         for (int sh = 16; sh > 0; sh >>= 1) st_units += __shfl_xor_sync(0xffffffffu, st_units, sh);
     if (tid == 0 && a.sc.stats) {
-        atomicAdd(&a.sc.stats[0], st_docs);
-        atomicAdd(&a.sc.stats[1], st_blocks);
-        atomicAdd(&a.sc.stats[2], st_pushed);
-        atomicAdd(&a.sc.stats[3], st_units);
+        atomicAdd(&a.sc.stats[0], (unsigned long long)st_docs);
+        atomicAdd(&a.sc.stats[1], (unsigned long long)st_blocks);
+        atomicAdd(&a.sc.stats[2], (unsigned long long)st_pushed);
+        atomicAdd(&a.sc.stats[3], (unsigned long long)st_units);
+        for (int i = 0; i < 6; ++i) atomicAdd(&a.sc.stats[4 + i], (unsigned long long)s_ph[i]);
     }
 }
 

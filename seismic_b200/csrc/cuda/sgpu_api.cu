@@ -86,13 +86,15 @@ struct SgpuIndex {
     uint32_t max_block_docs = 0;  // largest block
     // options
     uint32_t wave_docs = 2048, first_wave_docs = 256;       // dense-query kernel (1024 threads)
-    uint32_t hq_wave_docs = 384, hq_first_wave_docs = 64;  // hash-query kernel (128 threads)
+    uint32_t hq_wave_docs = 384, hq_first_wave_docs = 64;  // compact-query kernel (128 threads)
     int hq_enabled = 1, hq_ctas_per_sm = 0;
+    int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
+    int hq_threads = 256;
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
     // per-batch scratch (grow-only)
     DevBuf d_qoff, d_qcomps, d_qvals, d_nterms, d_status, d_counters, d_terms, d_est, d_order, d_keys, d_stats;
-    DevBuf d_out_ids, d_out_scores, d_out_counts, d_gdocs, d_gscores, d_hmult, d_qlist;
+    DevBuf d_out_ids, d_out_scores, d_out_counts, d_hmult, d_qlist;
     PinnedBuf h_in, h_out;
     ~SgpuIndex() {
         cudaSetDevice(device);
@@ -292,9 +294,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     CK(ix->d_nterms.ensure((size_t)nq * 4));
     CK(ix->d_status.ensure((size_t)nq * 4));
     CK(ix->d_counters.ensure(32));
-    CK(ix->d_stats.ensure(4 * sizeof(unsigned long long)));
+    CK(ix->d_stats.ensure(10 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ix->d_counters.p, 0, 32, st));
-    CK(cudaMemsetAsync(ix->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ix->d_stats.p, 0, 10 * sizeof(unsigned long long), st));
 
     CK(cudaEventRecord(ix->ev[0], st));
     Batch all{dq->offsets, dq->comps, dq->values, nq, 0};
@@ -324,58 +326,81 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     CK(ix->d_hmult.ensure((size_t)chunk * 4));
     CK(ix->d_qlist.ensure((size_t)chunk * 8));
 
-    // ---- launch plans of the two k_search instantiations
+    // ---- launch plans: the dense-query kernel (1 CTA / SM, any query) and the compact-query kernel
+    // (many CTAs / SM; bitmap+rank, byte-indexed or perfect-hash query)
     const size_t heap_bytes = 2 * (size_t)((k + 3) & ~3u) * 4;
-    SearchArgs ad{};  // dense-query kernel: 1 CTA / SM
+    const bool small_k = k <= 32;
+    SearchArgs ad{};
     ad.ix = ix->ix;
     ad.k = k;
     ad.heap_factor = p->heap_factor;
     ad.first_sorted = p->first_sorted ? 1 : 0;
     ad.wave_docs = std::max(1u, ix->wave_docs);
     ad.first_wave_docs = std::max(1u, ix->first_wave_docs);
-    ad.buf_docs = std::max(std::max(ad.wave_docs, ad.first_wave_docs), std::max(1u, ix->max_block_docs));
+    ad.buf_docs = std::max(ad.wave_docs, ad.first_wave_docs);
     ad.qd_words = (ix->ix.dim + 31u) & ~31u;
     ad.counter_idx = 0;
     const int ctas = std::max(1, ix->ctas);
-    const size_t fixed_d = (size_t)ad.qd_words * 4 + 3 * DENSE_THREADS * 4 + heap_bytes;
-    size_t smem_d = fixed_d + (size_t)ad.buf_docs * 12;
-    bool dense_ok = fixed_d + 1024 <= ix->smem_optin;
-    if (dense_ok && smem_d + 1024 > ix->smem_optin) {  // wave buffers spill to global scratch
-        CK(ix->d_gdocs.ensure((size_t)ctas * ad.buf_docs * 8));
-        CK(ix->d_gscores.ensure((size_t)ctas * ad.buf_docs * 4));
-        ad.g_docs = ix->d_gdocs.as<uint64_t>();
-        ad.g_scores = ix->d_gscores.as<float>();
-        smem_d = fixed_d;
-    }
-    auto kd = k_search<DENSE_THREADS, DenseQuery>;
-    auto kh = k_search<HQ_THREADS, HashQuery>;
+    auto wave_bytes = [&](const SearchArgs& x, int threads) {
+        return 3 * (size_t)threads * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
+    };
+    const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad, DENSE_THREADS);
+    const bool dense_ok = smem_d + 1024 <= ix->smem_optin;
+    typedef void (*kern_t)(const SearchArgs);
+    kern_t kd = small_k ? (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, RegHeap>
+                        : (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, SmemHeap>;
     if (dense_ok) CK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
 
-    SearchArgs ah = ad;  // hash-query kernel: several CTAs / SM
-    ah.g_docs = nullptr;
-    ah.g_scores = nullptr;
+    SearchArgs ah = ad;
     ah.wave_docs = std::max(1u, ix->hq_wave_docs);
     ah.first_wave_docs = std::max(1u, ix->hq_first_wave_docs);
-    ah.buf_docs = std::max(std::max(ah.wave_docs, ah.first_wave_docs), std::max(1u, ix->max_block_docs));
+    ah.buf_docs = std::max(ah.wave_docs, ah.first_wave_docs);
     ah.counter_idx = 3;
-    const size_t smem_h = (size_t)HQ_SLOTS * 6 + 3 * HQ_THREADS * 4 + heap_bytes + (size_t)ah.buf_docs * 12;
+    const int mode = ix->hq_mode;  // 1 byte index, 2 perfect hash, 3 bitmap + rank
+    const bool wide = ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
+    const int hq_threads = wide ? 256 : 128;
+    size_t qbytes = 0;
+    kern_t kh = nullptr;
+#define SGPU_PICK(Q, OCC128, D128)                                                                        \
+    (wide ? (small_k ? (kern_t)k_search<256, 4, 2, Q, RegHeap> : (kern_t)k_search<256, 4, 2, Q, SmemHeap>) \
+          : (small_k ? (kern_t)k_search<128, OCC128, D128, Q, RegHeap>                                     \
+                     : (kern_t)k_search<128, OCC128, D128, Q, SmemHeap>))
+    if (mode == 1) {
+        ah.qd_words = ((ix->ix.dim + 15u) / 16u) * 4u;
+        qbytes = 1024 + (size_t)ah.qd_words * 4;
+        kh = SGPU_PICK(ByteQuery, 6, 2);
+    } else if (mode == 2) {
+        qbytes = (size_t)HQ_SLOTS * 6;
+        kh = SGPU_PICK(HashQuery, 6, 2);
+    } else {
+        ah.qd_words = ((ix->ix.dim + 127u) / 128u) * 4u;
+        qbytes = 1024 + (size_t)ah.qd_words * 5;
+        kh = SGPU_PICK(RankQuery, 8, 2);
+    }
+#undef SGPU_PICK
+    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
     bool hq_ok = ix->hq_enabled && smem_h + 1024 <= ix->smem_optin / 2;  // at least 2 CTAs per SM or not worth it
     int hq_ctas = 0;
     if (hq_ok) {
         CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kh, HQ_THREADS, smem_h));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kh, hq_threads, smem_h));
         if (ix->hq_ctas_per_sm > 0) occ = std::min(occ, ix->hq_ctas_per_sm);
         hq_ok = occ >= 1;
         hq_ctas = occ * ix->n_sm;
     }
     if (!hq_ok && !dense_ok) {
-        shost::set_error("neither the hash-query nor the dense-query kernel fits this index in shared memory");
+        shost::set_error("neither the compact-query nor the dense-query kernel fits this index in shared memory");
         return SGPU_EUNSUPPORTED;
     }
-    // queries the hash path cannot take need the dense kernel
-    const uint32_t hq_max_nnz = hq_ok ? (dense_ok ? (uint32_t)HQ_MAX_NNZ : 0xffffffffu) : 0u;
-    const uint32_t hq_tries = dense_ok ? (uint32_t)HQ_TRIES : 4096u;
+    // routing (k_terms): queries the compact path cannot take need the dense kernel
+    const uint32_t max_nnz_compact = mode == 2 ? (uint32_t)HQ_MAX_NNZ : 255u;
+    if (hq_ok && !dense_ok && mode != 2) {
+        shost::set_error("compact queries hold <= 255 components and the dense kernel does not fit");
+        return SGPU_EUNSUPPORTED;
+    }
+    const uint32_t hq_max_nnz = hq_ok ? (dense_ok ? max_nnz_compact : 0xffffffffu) : 0u;
+    const uint32_t hq_tries = mode == 2 ? (dense_ok ? (uint32_t)HQ_TRIES : 4096u) : 0u;
 
     float ms_sum = 0.f, ms_search = 0.f, ms_fin = 0.f, ms_terms = 0.f;
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
@@ -417,7 +442,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         if (hq_ok) {
             ah.qlist = sc.qlist_hq;
             ah.n_list = sc.counters + 4;
-            kh<<<hq_ctas, HQ_THREADS, smem_h, st>>>(ah);
+            kh<<<hq_ctas, hq_threads, smem_h, st>>>(ah);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -445,8 +470,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     if (stats) {
         float ms_prep = 0.f;
         CK(cudaEventElapsedTime(&ms_prep, ix->ev[0], ix->ev[1]));
-        unsigned long long hs[4];
+        unsigned long long hs[10];
         CK(cudaMemcpy(hs, ix->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 6; ++i) stats->phase_cycles[i] = hs[4 + i];
         stats->ms_prep = ms_prep + ms_terms;
         stats->ms_summary = ms_sum;
         stats->ms_search = ms_search;
@@ -487,15 +513,17 @@ int sgpu_index_set_stream(SgpuIndex* ix, void* cuda_stream) {
 int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     if (!ix || !name) return SGPU_EINVAL;
     std::string n(name);
-    if (n == "hq") {
+    if (n == "hq") {  // 0: dense-query kernel only; compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
         ix->hq_enabled = value != 0;
+        if (value >= 1 && value <= 3) ix->hq_mode = (int)value;
         return SGPU_OK;
     }
     if (value <= 0) {
         shost::set_error("option values must be positive");
         return SGPU_EINVAL;
     }
-    if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
+    if (n == "hq_threads") ix->hq_threads = (int)value;
+    else if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
     else if (n == "hq_first_wave_docs") ix->hq_first_wave_docs = (uint32_t)value;
     else if (n == "hq_ctas_per_sm") ix->hq_ctas_per_sm = (int)value;
     else if (n == "wave_docs") ix->wave_docs = (uint32_t)value;

@@ -54,7 +54,7 @@ def test_parity_pruned(oracle_mod, synth_pruned, gpu_pruned, k, cut, hf, srt):
     assert gpu_pruned.last_stats["docs_scored"] >= ref[3]["docs_scored"]
 
 
-@pytest.mark.parametrize("hq", [1, 0])
+@pytest.mark.parametrize("hq", [3, 1, 2, 0])
 @pytest.mark.parametrize("wave,first", [(1, 1), (64, 8), (512, 512), (4096, 4096)])
 def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first, hq):
     """The speculative wave scheduler is a performance knob only: any wave size replays to the same heap,
@@ -64,14 +64,14 @@ def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first,
     g.set_option("hq", hq)
     g.set_option("wave_docs", wave)
     g.set_option("first_wave_docs", first)
-    g.set_option("hq_wave_docs", min(wave, 1024))
+    g.set_option("hq_wave_docs", min(wave, 1024))     # blocks larger than the wave buffer are split
     g.set_option("hq_first_wave_docs", min(first, 1024))
     ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 3, 0.8, first_sorted=True)
     got = g.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8, first_sorted=True)
     assert_same(got, ref, f"wave={wave}")
 
 
-@pytest.mark.parametrize("hq", [1, 0])
+@pytest.mark.parametrize("hq", [3, 1, 2, 0])
 def test_dense_and_hash_kernels_agree(oracle_mod, synth_small, hq):
     _, q, index = synth_small
     g = GpuIndex(index, 0)
