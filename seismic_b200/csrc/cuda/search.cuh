@@ -43,6 +43,9 @@ constexpr int DENSE_THREADS = 1024;
 #ifndef SGPU_LD256
 #define SGPU_LD256 0
 #endif
+#ifndef SGPU_SKIP_MISS
+#define SGPU_SKIP_MISS 1
+#endif
 
 __device__ __forceinline__ uint32_t hq_slot(uint32_t c, uint32_t mult) { return (c * mult) >> (32 - HQ_LOG2_SLOTS); }
 
@@ -121,8 +124,16 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
     float* vals;
     static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return 1024 + (size_t)a.qd_words * 4; }
     __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
+#if SGPU_SKIP_MISS
+        // components that are not in the query contribute +0.0: skipping them leaves acc bit-identical
+        const uint32_t i0 = qidx[cw & 0xffffu], i1 = qidx[cw >> 16];
+        if (i0) acc = __fadd_rn(acc, __fmul_rn(vals[i0], h_lo(vw)));
+        if (i1) acc = __fadd_rn(acc, __fmul_rn(vals[i1], h_hi(vw)));
+        return acc;
+#else
         acc = __fadd_rn(acc, __fmul_rn(vals[qidx[cw & 0xffffu]], h_lo(vw)));
         return __fadd_rn(acc, __fmul_rn(vals[qidx[cw >> 16]], h_hi(vw)));
+#endif
     }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {

@@ -86,7 +86,7 @@ struct SgpuIndex {
     uint32_t max_block_docs = 0;  // largest block
     // options
     uint32_t wave_docs = 2048, first_wave_docs = 256;       // dense-query kernel (1024 threads)
-    uint32_t hq_wave_docs = 384, hq_first_wave_docs = 64;  // compact-query kernel (128 threads)
+    uint32_t hq_wave_docs = 768, hq_first_wave_docs = 128;  // compact-query kernel
     int hq_enabled = 1, hq_ctas_per_sm = 0;
     int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
     int hq_threads = 256;
