@@ -36,8 +36,8 @@ sys.path.insert(0, str(REPO))
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=int(os.environ.get("SEISMIC_BENCH_DOCS", 8_800_000)))
     ap.add_argument("--dim", type=int, default=30522)
@@ -63,6 +63,16 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# Everything except the final JSON line goes to stderr: libraries (e.g. NCCL's version banner) write to fd 1.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe's clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -78,7 +88,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -193,7 +203,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if not a.keep_index:
         try:
             os.remove(path)
@@ -212,6 +222,7 @@ def main():
     import torch
     import torch.distributed as dist
     from seismic_b200 import GpuIndex, recall_at_k
+    from seismic_b200.distributed import pack_results
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -254,8 +265,7 @@ def main():
                                      a.heap_factor, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
                                      first_sorted=bool(a.sorted))
         if world > 1:  # single NCCL gather of the result tuples (ids u64 as 2 x i32, scores bits, counts)
-            packed = torch.cat([d_ids.view(torch.int32), d_sc.view(torch.int32), d_cnt.view(nq, 1)], dim=1)
-            dist.gather(packed, gathered if rank == 0 else None, dst=0)
+            dist.gather(pack_results(d_ids, d_sc, d_cnt), gathered if rank == 0 else None, dst=0)
         return st
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -371,7 +381,7 @@ def main():
             "phase_share": (lambda c: [round(x / max(1, sum(c)), 4) for x in c])(stats[-1]["phase_cycles"]),
             "setup_s": timings, "wall_s_timed_region": t_wall, "ms_kernels_per_step": ms_kernels,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     barrier()
     if world > 1:
         dist.destroy_process_group()

@@ -78,6 +78,7 @@ struct Scratch {
     uint32_t* counters;  // [0] dense work counter, [1] max nterms, [2] invalid queries, [3] hq work counter,
                          // [4] number of hq queries, [5] number of dense queries
     uint32_t* hmult;     // [nq] perfect-hash multiplier of the query (0: dense kernel)
+    uint32_t* cost;      // [nq] scheduling cost proxy (postings of the query's lists)
     uint32_t* qlist_hq;  // [nq] chunk-relative ids of the queries taken by the hash-query kernel
     uint32_t* qlist_dense;
     uint32_t* out_keys;  // [nq_chunk * k]
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(128) k_prep(Batch b, uint32_t dim, uint32_t qu
 // The same warp then routes the query: if it has <= hq_max_nnz components and a collision-free multiplier for
 // the HQ_SLOTS-slot hash table is found within HQ_TRIES attempts it goes to the hash-query kernel, else to the
 // dense-query kernel.
-__global__ void __launch_bounds__(128) k_terms(Batch b, Scratch sc, uint32_t hq_max_nnz, uint32_t hq_log2_slots,
-                                               uint32_t hq_tries) {
+__global__ void __launch_bounds__(128) k_terms(Batch b, Scratch sc, const ListHdr* __restrict__ lists,
+                                               uint32_t hq_max_nnz, uint32_t hq_log2_slots, uint32_t hq_tries) {
     __shared__ uint32_t s_bm[4][128];  // one 4096-bit occupancy map per warp
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + w;
@@ -174,8 +175,42 @@ __global__ void __launch_bounds__(128) k_terms(Batch b, Scratch sc, uint32_t hq_
     }
     if (lane == 0) {
         sc.hmult[q] = mult;
-        if (mult) sc.qlist_hq[atomicAdd(&sc.counters[4], 1u)] = q;
-        else sc.qlist_dense[atomicAdd(&sc.counters[5], 1u)] = q;
+        // cost proxy for longest-first scheduling: postings of the lists the query will walk
+        uint32_t cost = 0;
+        for (uint32_t t = 0; t < nt; ++t) cost += lists[sc.terms[(uint64_t)q * sc.cut_eff + t]].n_post;
+        sc.cost[q] = cost;
+    }
+}
+
+// Longest-first work lists: a counting sort of the chunk's queries by descending cost (64 buckets), one list per
+// k_search instantiation (compact / dense).  Single CTA; the order inside a bucket is irrelevant for results.
+constexpr int ROUTE_THREADS = 1024;
+constexpr int ROUTE_BUCKETS = 64;
+__global__ void __launch_bounds__(ROUTE_THREADS) k_route(Scratch sc, uint32_t nq, uint32_t cost_max) {
+    __shared__ uint32_t hist[2][ROUTE_BUCKETS], base[2][ROUTE_BUCKETS];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 2 * ROUTE_BUCKETS) (&hist[0][0])[tid] = 0;
+    __syncthreads();
+    const uint32_t div = cost_max / ROUTE_BUCKETS + 1;
+    for (uint32_t q = tid; q < nq; q += ROUTE_THREADS) {
+        const uint32_t bkt = min(sc.cost[q] / div, (uint32_t)ROUTE_BUCKETS - 1);
+        atomicAdd(&hist[sc.hmult[q] ? 0 : 1][bkt], 1u);
+    }
+    __syncthreads();
+    if (tid < 2) {
+        uint32_t acc = 0;
+        for (int bkt = ROUTE_BUCKETS - 1; bkt >= 0; --bkt) {
+            base[tid][bkt] = acc;
+            acc += hist[tid][bkt];
+        }
+        sc.counters[4 + tid] = acc;
+    }
+    __syncthreads();
+    for (uint32_t q = tid; q < nq; q += ROUTE_THREADS) {
+        const uint32_t kind = sc.hmult[q] ? 0 : 1;
+        const uint32_t bkt = min(sc.cost[q] / div, (uint32_t)ROUTE_BUCKETS - 1);
+        const uint32_t slot = atomicAdd(&base[kind][bkt], 1u);
+        (kind ? sc.qlist_dense : sc.qlist_hq)[slot] = q;
     }
 }
 
@@ -188,7 +223,7 @@ __global__ void __launch_bounds__(128) k_terms(Batch b, Scratch sc, uint32_t hq_
 // global scratch (same algorithm, L2-coherent accesses).
 // ------------------------------------------------------------------------------------------
 constexpr int EST_WARPS = 4;
-constexpr int EST_SMEM = 2048;  // blocks per warp kept in shared memory (4 x 8 KB)
+constexpr int EST_SMEM = 1024;  // blocks per warp kept in shared memory (4 x 4 KB); larger lists accumulate in global
 
 __global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc) {
     __shared__ float s_est[EST_WARPS][EST_SMEM];

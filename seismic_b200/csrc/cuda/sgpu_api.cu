@@ -84,6 +84,7 @@ struct SgpuIndex {
     uint64_t image_bytes = 0;
     uint32_t max_blocks = 0;      // largest number of blocks of any list
     uint32_t max_block_docs = 0;  // largest block
+    uint32_t max_list_post = 0;   // longest posting list
     // options
     uint32_t wave_docs = 2048, first_wave_docs = 256;       // dense-query kernel (1024 threads)
     uint32_t hq_wave_docs = 768, hq_first_wave_docs = 128;  // compact-query kernel
@@ -221,6 +222,7 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
             return SGPU_EINVAL;
         }
         max_blocks = std::max(max_blocks, h.n_blk);
+        ix->max_list_post = std::max(ix->max_list_post, h.n_post);
         const uint32_t* bo = v->blk_post_off + h.blk_base + l;
         for (uint32_t b = 0; b < h.n_blk; ++b) max_block_docs = std::max(max_block_docs, bo[b + 1] - bo[b]);
     }
@@ -323,7 +325,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     CK(ix->d_est.ensure((size_t)chunk * cut_eff * est_stride * 4));
     CK(ix->d_order.ensure((size_t)chunk * est_stride * 2));
     CK(ix->d_keys.ensure((size_t)chunk * k * 4));
-    CK(ix->d_hmult.ensure((size_t)chunk * 4));
+    CK(ix->d_hmult.ensure((size_t)chunk * 8));
     CK(ix->d_qlist.ensure((size_t)chunk * 8));
 
     // ---- launch plans: the dense-query kernel (1 CTA / SM, any query) and the compact-query kernel
@@ -414,6 +416,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         sc.order = ix->d_order.as<uint16_t>();
         sc.counters = ix->d_counters.as<uint32_t>();
         sc.hmult = ix->d_hmult.as<uint32_t>();
+        sc.cost = ix->d_hmult.as<uint32_t>() + chunk;
         sc.qlist_hq = ix->d_qlist.as<uint32_t>();
         sc.qlist_dense = ix->d_qlist.as<uint32_t>() + chunk;
         sc.out_keys = ix->d_keys.as<uint32_t>();
@@ -422,8 +425,11 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         sc.cut_eff = cut_eff;
         CK(cudaMemsetAsync(ix->d_counters.p, 0, 32, st));
         CK(cudaEventRecord(ix->ev[2], st));
-        k_terms<<<(n + 3) / 4, 128, 0, st>>>(b, sc, hq_max_nnz, (uint32_t)HQ_LOG2_SLOTS, hq_tries);
+        k_terms<<<(n + 3) / 4, 128, 0, st>>>(b, sc, ix->ix.lists, hq_max_nnz, (uint32_t)HQ_LOG2_SLOTS, hq_tries);
         CK(cudaGetLastError());
+        k_route<<<1, ROUTE_THREADS, 0, st>>>(sc, n, cut_eff * ix->max_list_post);
+        CK(cudaGetLastError());
+        ++launches;
         CK(cudaEventRecord(ix->ev[3], st));
         const uint64_t tasks = (uint64_t)n * cut_eff;
         k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);

@@ -82,6 +82,21 @@ def test_dense_and_hash_kernels_agree(oracle_mod, synth_small, hq):
         assert_same(got, ref, f"hq={hq} k={k}")
 
 
+def test_lists_with_thousands_of_blocks(oracle_mod):
+    """centroid_fraction 0.5 gives lists with > 1024 blocks: k_est accumulates in global memory instead of shared
+    memory, k_order sorts up to 4096 keys, and selection needs several rounds of 256 positions per list."""
+    from conftest import build_synth
+    _, q, index = build_synth(20000, 200, dim=300, n_postings=3000, centroid_fraction=0.5, max_fraction=2.0,
+                              min_cluster_size=0)
+    a = index.arrays()
+    assert int(np.diff(a["list_blk_start"]).max()) > 1024
+    g = GpuIndex(index, 0)
+    for srt in (True, False):
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 4, 0.9, first_sorted=srt)
+        got = g.batch_search(q.offsets, q.comps, q.values, 10, 4, 0.9, first_sorted=srt)
+        assert_same(got, ref, f"many blocks sorted={srt}")
+
+
 def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
     _, q, index = synth_small
     g = GpuIndex(index, 0)
