@@ -59,6 +59,7 @@ struct DevIndex {
     const uint32_t* rec_start;  // [n_docs+1]
     uint64_t n_docs;
     uint32_t dim;
+    uint32_t comp32;  // 1: u32 components (Rec32 records, 16-byte units), 0: u16 components (Rec16, 32-byte units)
 };
 
 struct Batch {
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(128) k_prep(Batch b, uint32_t dim, uint32_t qu
         status[q] = bad ? 1u : 0u;
         atomicMax(&counters[1], nt);
         if (bad) atomicAdd(&counters[2], 1u);
+        atomicMax(&counters[6], (uint32_t)(n < 0xffffffffull ? n : 0xffffffffull));
     }
 }
 
@@ -379,6 +381,24 @@ __global__ void k_pack_records(const uint64_t* fwd_off, const uint16_t* comps, c
         const bool ok = i < len;
         rec[ch * 16 + j] = ok ? comps[e0 - elem0 + i] : (uint16_t)0;
         rec[ch * 16 + 8 + j] = ok ? vals[e0 - elem0 + i] : (uint16_t)0;
+    }
+}
+
+// u32 components: chunk = 8 x u32 components followed by 8 x f16 values (48 bytes); rec_start counts 16-byte units
+__global__ void k_pack_records32(const uint64_t* fwd_off, const uint32_t* comps, const uint16_t* vals,
+                                 const uint32_t* rec_start, uint64_t doc0, uint64_t n_docs_chunk, uint64_t elem0,
+                                 uint32_t* records /* base of the whole record buffer */) {
+    const uint64_t d = doc0 + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d >= doc0 + n_docs_chunk) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t e0 = fwd_off[d], len = fwd_off[d + 1] - e0;
+    const uint32_t nch = (uint32_t)((len + 7) >> 3);
+    uint32_t* rec = records + (uint64_t)rec_start[d] * 4;
+    for (uint32_t i = lane; i < nch * 8; i += 32) {
+        const uint32_t ch = i >> 3, j = i & 7;
+        const bool ok = i < len;
+        rec[ch * 12 + j] = ok ? comps[e0 - elem0 + i] : 0u;
+        reinterpret_cast<uint16_t*>(rec + ch * 12 + 8)[j] = ok ? vals[e0 - elem0 + i] : (uint16_t)0;
     }
 }
 

@@ -256,24 +256,52 @@ struct RankQuery {
     }
 };
 
-// acc += q[c] * v for the 8 (component, value) pairs of one chunk, ascending
-template <class Q>
-__device__ __forceinline__ float chunk_dot(float acc, const uint4 c, const uint4 v, const Q& q) {
-    acc = q.mac2(acc, c.x, v.x);
-    acc = q.mac2(acc, c.y, v.y);
-    acc = q.mac2(acc, c.z, v.z);
-    return q.mac2(acc, c.w, v.w);
-}
+// ---- forward-index record layouts ---------------------------------------------------------------------------
+// A record is a sequence of chunks of 8 (component, value) pairs; the posting's start field counts UNIT-byte units.
+struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x uint4, unit 32 bytes
+    static constexpr int U = 2;          // uint4 per chunk
+    static constexpr int START_MUL = 2;  // uint4 per unit of the posting's start field
+    struct Chunk { uint4 c, v; };
+    static __device__ __forceinline__ void load(const uint4* p, Chunk& k) { ld_chunk(p, k.c, k.v); }
+    template <class Q>
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q) {
+        acc = q.mac2(acc, k.c.x, k.v.x);
+        acc = q.mac2(acc, k.c.y, k.v.y);
+        acc = q.mac2(acc, k.c.z, k.v.z);
+        return q.mac2(acc, k.c.w, k.v.w);
+    }
+};
+struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16] = 48 bytes = 3 x uint4, unit 16 bytes
+    static constexpr int U = 3;
+    static constexpr int START_MUL = 1;
+    struct Chunk { uint4 c0, c1, v; };
+    static __device__ __forceinline__ void load(const uint4* p, Chunk& k) {
+        k.c0 = ld_stream(p);
+        k.c1 = ld_stream(p + 1);
+        k.v = ld_stream(p + 2);
+    }
+    template <class Q>
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q) {
+        acc = q.mac(acc, k.c0.x, k.v.x, false);
+        acc = q.mac(acc, k.c0.y, k.v.x, true);
+        acc = q.mac(acc, k.c0.z, k.v.y, false);
+        acc = q.mac(acc, k.c0.w, k.v.y, true);
+        acc = q.mac(acc, k.c1.x, k.v.z, false);
+        acc = q.mac(acc, k.c1.y, k.v.z, true);
+        acc = q.mac(acc, k.c1.z, k.v.w, false);
+        return q.mac(acc, k.c1.w, k.v.w, true);
+    }
+};
 
-// Score one document record (nch 32-byte chunks at `rec`) with an 8-lane group; lane8 handles chunks
+// Score one document record (nch chunks at `rec`) with an 8-lane group; lane8 handles chunks
 // lane8, lane8+8, ...  The caller reduces the 8 partial sums with group_reduce.
-template <class Q>
+template <class R, class Q>
 __device__ __forceinline__ float score_rec(const uint4* __restrict__ rec, uint32_t nch, uint32_t lane8, const Q& q) {
     float acc = 0.f;
     for (uint32_t m = lane8; m < nch; m += 8) {
-        uint4 c, v;
-        ld_chunk(rec + 2 * m, c, v);
-        acc = chunk_dot(acc, c, v, q);
+        typename R::Chunk k;
+        R::load(rec + R::U * m, k);
+        acc = R::dot(acc, k, q);
     }
     return acc;
 }
@@ -285,26 +313,26 @@ __device__ __forceinline__ float group_reduce(float s) {
 
 // Score D documents with one 8-lane group, round by round: in round r lane8 handles chunk lane8 + 8r of every
 // document; all loads of a round are issued before the first use.  `rounds` must be warp-uniform.
-template <int D, class Q>
+template <int D, class R, class Q>
 __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const uint64_t (&post)[D], uint32_t lane8,
                                            uint32_t rounds, const Q& q, float (&acc)[D]) {
     const uint4* rec[D];
     uint32_t nch[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        rec[j] = fwd + (post[j] >> 16) * 2 + 2 * lane8;
+        rec[j] = fwd + (post[j] >> 16) * R::START_MUL + R::U * lane8;
         nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
         acc[j] = 0.f;
     }
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t m = lane8 + 8 * r;
-        uint4 c[D], v[D];
+        typename R::Chunk k[D];
 #pragma unroll
         for (int j = 0; j < D; ++j)
-            if (m < nch[j]) ld_chunk(rec[j] + 16 * r, c[j], v[j]);
+            if (m < nch[j]) R::load(rec[j] + R::U * 8 * r, k[j]);
 #pragma unroll
         for (int j = 0; j < D; ++j)
-            if (m < nch[j]) acc[j] = chunk_dot(acc[j], c[j], v[j], q);
+            if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q);
     }
 }
 
@@ -418,8 +446,9 @@ struct SmemHeap {
 
 // -----------------------------------------------------------------------------------------------------------
 // T threads per CTA, OCC = CTAs per SM the register allocation is budgeted for, D = documents per 8-lane group
-// per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise).
-template <int T, int OCC, int D, class Q, class H>
+// per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise),
+// R = record layout (Rec16: u16 components, Rec32: u32 components).
+template <int T, int OCC, int D, class Q, class H, class R = Rec16>
 __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     constexpr int NW = T / 32;      // warps
     constexpr int GROUPS = T / 8;   // 8-lane groups
@@ -480,13 +509,14 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             }
             const uint32_t rounds = (__reduce_max_sync(0xffffffffu, mx) + 63) >> 6;
             float acc[D];
-            score_docs<D>(a.ix.fwd, post, lane8, rounds, query, acc);
+            score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, acc);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const float s = group_reduce(acc[j]);
                 const uint32_t d = dbase + j * GROUPS + grp;
                 if (lane8 == 0 && d < n) {
                     scores[d] = s;
+                    st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
                     // theta only grows: a document that cannot enter the heap as of the wave start never will
                     if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey))
                         atomicOr(&surv[d >> 5], 1u << (d & 31));
@@ -600,7 +630,6 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         __syncthreads();
                         if (warp == 0) {
                             st_docs += part;
-                            for (uint32_t i = lane; i < part; i += 32) st_units += ((uint32_t)(docs[i] & 0xffffu) + 7) >> 3;
                             push_range(0, part);
                             if (lane == 0) s_full = heap.full(), s_theta = heap.theta, s_wkey = heap.wkey;
                         }
@@ -638,7 +667,6 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 if (warp == 0) {
                     st_docs += n_docs;
                     st_blocks += n_cand;
-                    for (uint32_t i = lane; i < n_docs; i += 32) st_units += ((uint32_t)(docs[i] & 0xffffu) + 7) >> 3;
                     // 32 candidate blocks at a time: blocks without survivors only need the skip test (counted,
                     // heap untouched); the first block WITH survivors that passes the test against the live theta
                     // is pushed, which may raise theta, so the scan restarts right after it.
@@ -684,8 +712,8 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         if (nt > 0) query.template unstage<T>(a.b, qo, qn, tid);
         lap(5);
     }
-    if (warp == 0)
-        for (int sh = 16; sh > 0; sh >>= 1) st_units += __shfl_xor_sync(0xffffffffu, st_units, sh);
+    for (int sh = 16; sh > 0; sh >>= 1) st_units += __shfl_xor_sync(0xffffffffu, st_units, sh);
+    if (lane == 0 && warp != 0 && a.sc.stats) atomicAdd(&a.sc.stats[3], (unsigned long long)st_units);
     if (tid == 0 && a.sc.stats) {
         atomicAdd(&a.sc.stats[0], (unsigned long long)st_docs);
         atomicAdd(&a.sc.stats[1], (unsigned long long)st_blocks);

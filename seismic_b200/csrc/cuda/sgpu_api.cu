@@ -120,12 +120,13 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
         shost::set_error("sgpu_index_create: null argument");
         return SGPU_EINVAL;
     }
-    if (v->comp_bits != 16 || v->value_kind != SGPU_VAL_F16) {
-        shost::set_error("sgpu_index_create: this build supports u16 components with f16 values");
+    if ((v->comp_bits != 16 && v->comp_bits != 32) || v->value_kind != SGPU_VAL_F16) {
+        shost::set_error("sgpu_index_create: this build supports u16/u32 components with f16 values");
         return SGPU_EUNSUPPORTED;
     }
-    if (v->dim > 65536 || v->dim == 0) {
-        shost::set_error("sgpu_index_create: dim must be in [1, 65536] for u16 components");
+    const bool comp32 = v->comp_bits == 32;
+    if (v->dim == 0 || (!comp32 && v->dim > 65536) || v->dim > (1u << 20)) {
+        shost::set_error("sgpu_index_create: dim must be in [1, 65536] for u16 and [1, 2^20] for u32 components");
         return SGPU_EINVAL;
     }
     int ndev = 0;
@@ -163,15 +164,15 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
                 shost::set_error("document longer than 65535 components");
                 return SGPU_EINVAL;
             }
-            units += (len + 7) >> 3;
+            units += ((len + 7) >> 3) * (comp32 ? 3 : 1);
             if (units >= (1ull << 32)) {
-                shost::set_error("forward index larger than 2^32 32-byte units");
+                shost::set_error("forward index larger than 2^32 record units");
                 return SGPU_EUNSUPPORTED;
             }
         }
         rec_start[N] = (uint32_t)units;
-        CK(ix->fwd.ensure(std::max<uint64_t>(units, 1) * 32));
-        total += units * 32;
+        CK(ix->fwd.ensure(std::max<uint64_t>(units, 1) * (comp32 ? 16 : 32)));
+        total += units * (comp32 ? 16 : 32);
     }
     if (int rc = upload(ix->rec_start, rec_start.data(), N + 1, st, &total)) return rc;
     DevBuf d_fwd_off;
@@ -187,16 +188,21 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
             while (d1 < N && v->fwd_offsets[d1 + 1] - e0 <= slice_elems) ++d1;
             if (d1 == d0) d1 = d0 + 1;
             const uint64_t ne = v->fwd_offsets[d1] - e0;
-            CK(d_c.ensure(std::max<uint64_t>(ne, 1) * 2));
+            CK(d_c.ensure(std::max<uint64_t>(ne, 1) * (comp32 ? 4 : 2)));
             CK(d_v.ensure(std::max<uint64_t>(ne, 1) * 2));
             if (ne) {
-                CK(cudaMemcpyAsync(d_c.p, (const uint16_t*)v->fwd_comps + e0, ne * 2, cudaMemcpyHostToDevice, st));
+                if (comp32) CK(cudaMemcpyAsync(d_c.p, (const uint32_t*)v->fwd_comps + e0, ne * 4, cudaMemcpyHostToDevice, st));
+                else CK(cudaMemcpyAsync(d_c.p, (const uint16_t*)v->fwd_comps + e0, ne * 2, cudaMemcpyHostToDevice, st));
                 CK(cudaMemcpyAsync(d_v.p, (const uint16_t*)v->fwd_values + e0, ne * 2, cudaMemcpyHostToDevice, st));
             }
             const uint64_t nd = d1 - d0;
             const unsigned blocks = (unsigned)((nd + 7) / 8);
-            k_pack_records<<<blocks, 256, 0, st>>>(d_fwd_off.as<uint64_t>(), d_c.as<uint16_t>(), d_v.as<uint16_t>(),
-                                                   ix->rec_start.as<uint32_t>(), d0, nd, e0, ix->fwd.as<uint16_t>());
+            if (comp32)
+                k_pack_records32<<<blocks, 256, 0, st>>>(d_fwd_off.as<uint64_t>(), d_c.as<uint32_t>(), d_v.as<uint16_t>(),
+                                                         ix->rec_start.as<uint32_t>(), d0, nd, e0, ix->fwd.as<uint32_t>());
+            else
+                k_pack_records<<<blocks, 256, 0, st>>>(d_fwd_off.as<uint64_t>(), d_c.as<uint16_t>(), d_v.as<uint16_t>(),
+                                                       ix->rec_start.as<uint32_t>(), d0, nd, e0, ix->fwd.as<uint16_t>());
             CK(cudaGetLastError());
             CK(cudaStreamSynchronize(st));
             d0 = d1;
@@ -258,6 +264,7 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     d.rec_start = ix->rec_start.as<uint32_t>();
     d.n_docs = N;
     d.dim = (uint32_t)dim;
+    d.comp32 = comp32 ? 1u : 0u;
     *out = ix.release();
     return SGPU_OK;
 }
@@ -306,9 +313,10 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
                                          ix->d_status.as<uint32_t>(), ix->d_counters.as<uint32_t>());
     CK(cudaGetLastError());
     ++launches;
-    uint32_t h_counters[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(h_counters, ix->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+    uint32_t h_all[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_all, ix->d_counters.p, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const uint32_t h_counters[4] = {h_all[0], h_all[1], h_all[2], h_all[6]};  // [3] = largest query nnz
     if (h_counters[2] != 0) {
         shost::set_error("Query components must be sorted in ascending order and be < dim (" +
                          std::to_string(h_counters[2]) + " invalid queries)");
@@ -347,7 +355,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         return 3 * (size_t)threads * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
     };
     const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad, DENSE_THREADS);
-    const bool dense_ok = smem_d + 1024 <= ix->smem_optin;
+    const bool comp32 = ix->ix.comp32 != 0;
+    const bool dense_ok = !comp32 && smem_d + 1024 <= ix->smem_optin;
     typedef void (*kern_t)(const SearchArgs);
     kern_t kd = small_k ? (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, RegHeap>
                         : (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, SmemHeap>;
@@ -358,8 +367,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ah.first_wave_docs = std::max(1u, ix->hq_first_wave_docs);
     ah.buf_docs = std::max(ah.wave_docs, ah.first_wave_docs);
     ah.counter_idx = 3;
-    const int mode = ix->hq_mode;  // 1 byte index, 2 perfect hash, 3 bitmap + rank
-    const bool wide = ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
+    const int mode = comp32 ? 3 : ix->hq_mode;  // 1 byte index, 2 perfect hash, 3 bitmap + rank (only choice for u32)
+    const bool wide = comp32 || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
     const int hq_threads = wide ? 256 : 128;
     size_t qbytes = 0;
     kern_t kh = nullptr;
@@ -378,10 +387,13 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         ah.qd_words = ((ix->ix.dim + 127u) / 128u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 5;
         kh = SGPU_PICK(RankQuery, 8, 2);
+        if (comp32)
+            kh = small_k ? (kern_t)k_search<256, 4, 2, RankQuery, RegHeap, Rec32>
+                         : (kern_t)k_search<256, 4, 2, RankQuery, SmemHeap, Rec32>;
     }
 #undef SGPU_PICK
     const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
-    bool hq_ok = ix->hq_enabled && smem_h + 1024 <= ix->smem_optin / 2;  // at least 2 CTAs per SM or not worth it
+    bool hq_ok = (comp32 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
     if (hq_ok) {
         CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
@@ -397,8 +409,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     }
     // routing (k_terms): queries the compact path cannot take need the dense kernel
     const uint32_t max_nnz_compact = mode == 2 ? (uint32_t)HQ_MAX_NNZ : 255u;
-    if (hq_ok && !dense_ok && mode != 2) {
-        shost::set_error("compact queries hold <= 255 components and the dense kernel does not fit");
+    if (hq_ok && !dense_ok && mode != 2 && h_counters[3] > 255) {
+        shost::set_error("queries with more than 255 components need the dense-query kernel, which does not fit "
+                         "this vocabulary in shared memory");
         return SGPU_EUNSUPPORTED;
     }
     const uint32_t hq_max_nnz = hq_ok ? (dense_ok ? max_nnz_compact : 0xffffffffu) : 0u;
@@ -488,7 +501,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         stats->docs_scored = hs[0];
         stats->blocks_scored = hs[1];
         stats->blocks_pushed = hs[2];
-        stats->fwd_bytes = hs[3] * 32ull;
+        stats->fwd_bytes = hs[3] * (ix->ix.comp32 ? 48ull : 32ull);
     }
     return SGPU_OK;
 }
@@ -607,6 +620,10 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
     if (!ix || !q || !out_ids || !out_scores || !out_counts || k == 0 || k > 1024) {
         shost::set_error("sgpu_exact_search: bad argument");
         return SGPU_EINVAL;
+    }
+    if (ix->ix.comp32) {
+        shost::set_error("sgpu_exact_search: not available for u32-component indexes");
+        return SGPU_EUNSUPPORTED;
     }
     CK(cudaSetDevice(ix->device));
     const uint64_t nq = q->n_queries;

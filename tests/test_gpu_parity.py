@@ -97,6 +97,36 @@ def test_lists_with_thousands_of_blocks(oracle_mod):
         assert_same(got, ref, f"many blocks sorted={srt}")
 
 
+@pytest.fixture(scope="module")
+def synth_lv():
+    """Large-vocabulary index: 120 k vocabulary, u32 components (SeismicIndexLV)."""
+    from conftest import build_synth
+    return build_synth(30000, 300, dim=120000, comp_bits=32, n_postings=200, centroid_fraction=0.2)
+
+
+@pytest.mark.parametrize("k,cut,hf,srt", [(10, 3, 0.8, True), (100, 5, 0.9, True), (100, 8, 0.8, False), (7, 2, 1.0, True)])
+def test_parity_large_vocabulary(oracle_mod, synth_lv, k, cut, hf, srt):
+    _, q, index = synth_lv
+    assert index.comp_bits == 32 and index.dim == 120000
+    g = GpuIndex(index, 0)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    assert_same(got, ref, f"LV k={k} cut={cut} hf={hf} sorted={srt}")
+    assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
+def test_large_vocabulary_query_limit(synth_lv):
+    """u32 indexes only have the compact (bitmap + rank) query kernel: > 255 components per query is refused."""
+    docs, q, index = synth_lv
+    g = GpuIndex(index, 0)
+    qc = np.arange(0, 3000, 10, dtype=np.uint32)          # 300 components
+    with pytest.raises(NotImplementedError):
+        g.batch_search(np.array([0, len(qc)], np.uint64), qc, np.ones(len(qc), np.float32), 10, 3, 0.8)
+    qc = qc[:255]
+    ids, scores, counts = g.batch_search(np.array([0, len(qc)], np.uint64), qc, np.ones(len(qc), np.float32), 10, 3, 0.8)
+    assert counts[0] <= 10
+
+
 def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
     _, q, index = synth_small
     g = GpuIndex(index, 0)
