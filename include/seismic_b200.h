@@ -238,6 +238,9 @@ int shost_synth_queries(const ShostSynthConfig* cfg, uint64_t n_queries, ShostDa
 
 /* index build / persistence */
 int shost_index_build(const ShostDataset* ds, const ShostBuildConfig* cfg, ShostIndex** out);
+/* u16/f16 index -> same posting lists over a DotVByte forward index (gap-coded components, u8 values);
+ * reference: src/pylib/dotvbyte.rs:195-213 + convert_dataset_from, src/inverted_index.rs:237-275 */
+int shost_index_convert_dotvbyte(const ShostIndex* idx, ShostIndex** out);
 int shost_index_save(const ShostIndex* idx, const char* path);
 int shost_index_load(const char* path, ShostIndex** out); /* mmap, zero copy                      */
 void shost_index_destroy(ShostIndex* idx);

@@ -238,10 +238,51 @@ float doc_score_t(const SgpuIndexView& v, const float* q, uint64_t start, uint32
     }
     return ((p[0] + p[4]) + (p[2] + p[6])) + ((p[1] + p[5]) + (p[3] + p[7]));
 }
+// DotVByte record (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte): `start` counts 4-byte units of the
+// packed stream, `len` is the number of components.  value = code * scale, then the same accumulation as above.
+inline uint32_t vb_record_bytes(const SgpuIndexView& v, uint64_t start, uint32_t len) {
+    const uint8_t* rec = (const uint8_t*)v.fwd_values + start * 4;
+    const uint32_t nch = (len + 7) >> 3;
+    const uint8_t* ctrl = rec + ((2 * nch + 3) & ~3u);
+    uint32_t bytes = ((2 * nch + 3) & ~3u) + ((nch + 3) & ~3u) + 8 * nch + 7 * nch;
+    for (uint32_t m = 0; m < nch; ++m) bytes += __builtin_popcount(ctrl[m]);
+    return bytes;
+}
+template <int ORDER>
+float doc_score_vbyte(const SgpuIndexView& v, const float* q, uint64_t start, uint32_t len) {
+    const uint8_t* rec = (const uint8_t*)v.fwd_values + start * 4;
+    const uint32_t nch = (len + 7) >> 3;
+    const uint16_t* base = (const uint16_t*)rec;
+    const uint8_t* ctrl = rec + ((2 * nch + 3) & ~3u);
+    const uint8_t* vv = ctrl + ((nch + 3) & ~3u);
+    const uint8_t* gp = vv + 8 * nch;
+    float p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seq = 0.f;
+    for (uint32_t m = 0; m < nch; ++m) {
+        uint32_t c = base[m];
+        for (uint32_t j = 0; j < 8; ++j) {
+            if (j) {
+                uint32_t gap = *gp++;
+                if ((ctrl[m] >> j) & 1) gap |= (uint32_t)(*gp++) << 8;
+                c += gap;
+            }
+            if (m * 8 + j >= len) continue;  // tail padding: gap 0, code 0
+            const float val = (float)vv[m * 8 + j] * v.value_scale;
+            if (ORDER == ORDER_SEQ) seq = seq + q[c] * val;
+            else p[m & 7] = p[m & 7] + q[c] * val;
+        }
+    }
+    if (ORDER == ORDER_SEQ) return seq;
+    return ((p[0] + p[4]) + (p[2] + p[6])) + ((p[1] + p[5]) + (p[3] + p[7]));
+}
 template <int ORDER>
 inline float doc_score(const SgpuIndexView& v, const float* q, uint64_t start, uint32_t len) {
+    if (v.value_kind == SGPU_VAL_DOTVBYTE) return doc_score_vbyte<ORDER>(v, q, start, len);
     return v.comp_bits == 16 ? doc_score_t<ORDER, uint16_t>(v, q, start, len)
                              : doc_score_t<ORDER, uint32_t>(v, q, start, len);
+}
+// forward-index position (fwd_offsets units: elements, or bytes for DotVByte) of a posting's start field
+inline uint64_t fwd_pos(const SgpuIndexView& v, uint64_t start) {
+    return v.value_kind == SGPU_VAL_DOTVBYTE ? start * 4 : start;
 }
 
 inline uint32_t bits_for(uint64_t n_values) {  // BitField width for values in [0, n_values)
@@ -292,6 +333,7 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
                 Ctx& cx, uint64_t* out_ids, float* out_scores, uint32_t* out_count) {
     OracleStats& st = cx.st;
     const uint32_t cbytes = v.comp_bits / 8, vbytes = value_bytes(v.value_kind);
+    const bool vbyte = v.value_kind == SGPU_VAL_DOTVBYTE;
     float* q = cx.qdense.data();
     for (uint64_t i = 0; i < nq; ++i) q[qc[i]] = qv[i];  // dense evaluator; last duplicate wins
     st.bytes_query_out += nq * (cbytes + 4);
@@ -339,15 +381,19 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
             for (uint64_t i = p0; i < p1; ++i) {  // prefetch pass (src/posting_list.rs:198-204)
                 uint64_t start = posts[i] >> 16;
                 if (cx.visited.contains(start)) continue;
-                __builtin_prefetch((const uint8_t*)v.fwd_comps + start * cbytes);
-                __builtin_prefetch((const uint8_t*)v.fwd_values + start * vbytes);
+                if (vbyte) {
+                    __builtin_prefetch((const uint8_t*)v.fwd_values + start * 4);
+                } else {
+                    __builtin_prefetch((const uint8_t*)v.fwd_comps + start * cbytes);
+                    __builtin_prefetch((const uint8_t*)v.fwd_values + start * vbytes);
+                }
             }
             for (uint64_t i = p0; i < p1; ++i) {
                 uint64_t start = posts[i] >> 16;
                 uint32_t len = (uint32_t)(posts[i] & 0xffff);
                 if (cx.visited.insert(start)) {
                     st.docs_scored++;
-                    st.bytes_forward += (uint64_t)len * (cbytes + vbytes);
+                    st.bytes_forward += vbyte ? vb_record_bytes(v, start, len) : (uint64_t)len * (cbytes + vbytes);
                     heap.push(Item{doc_score<ORDER>(v, q, start, len), start, len});
                 }
             }
@@ -361,7 +407,7 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
         if (i < res.size()) {
             // id_from_range: the doc whose range starts here; duplicate offsets (empty docs) resolve to
             // the non-empty one (pinned by src/inverted_index.rs:716-772)
-            const uint64_t* ub = std::upper_bound(v.fwd_offsets, v.fwd_offsets + v.n_docs + 1, res[i].start);
+            const uint64_t* ub = std::upper_bound(v.fwd_offsets, v.fwd_offsets + v.n_docs + 1, fwd_pos(v, res[i].start));
             out_ids[i] = (uint64_t)(ub - v.fwd_offsets) - 1;
             out_scores[i] = res[i].score;
         } else {
@@ -375,7 +421,7 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
 int validate(const SgpuIndexView* v, const SgpuQueryBatch* qb, const SgpuSearchParams* p) {
     if (!v || !qb || !p || p->k == 0) return SGPU_EINVAL;
     if (p->n_knn != 0) return SGPU_EUNSUPPORTED;
-    if (v->value_kind == SGPU_VAL_DOTVBYTE) return SGPU_EUNSUPPORTED;
+    if (v->value_kind == SGPU_VAL_DOTVBYTE && (v->comp_bits != 16 || !v->fwd_nnz)) return SGPU_EUNSUPPORTED;
     for (uint64_t qi = 0; qi < qb->n_queries; ++qi)
         for (uint64_t i = qb->offsets[qi]; i < qb->offsets[qi + 1]; ++i) {
             if (qb->comps[i] >= v->dim) return SGPU_EINVAL;
@@ -489,6 +535,7 @@ int oracle_exact_search(const SgpuIndexView* v, const SgpuQueryBatch* qb, uint32
                 for (uint64_t d = 0; d < v->n_docs; ++d) {
                     uint64_t s = v->fwd_offsets[d];
                     uint32_t len = (uint32_t)(v->fwd_offsets[d + 1] - s);
+                    if (v->value_kind == SGPU_VAL_DOTVBYTE) s >>= 2, len = v->fwd_nnz[d];
                     if (!len) continue;
                     heap.push(Item{doc_score<ORDER_LANES8>(*v, q.data(), s, len), s, len});
                 }
@@ -496,7 +543,7 @@ int oracle_exact_search(const SgpuIndexView* v, const SgpuQueryBatch* qb, uint32
                 out_counts[qi] = (uint32_t)res.size();
                 for (uint32_t i = 0; i < k; ++i) {
                     if (i < res.size()) {
-                        const uint64_t* ub = std::upper_bound(v->fwd_offsets, v->fwd_offsets + v->n_docs + 1, res[i].start);
+                        const uint64_t* ub = std::upper_bound(v->fwd_offsets, v->fwd_offsets + v->n_docs + 1, fwd_pos(*v, res[i].start));
                         out_ids[qi * k + i] = (uint64_t)(ub - v->fwd_offsets) - 1;
                         out_scores[qi * k + i] = res[i].score;
                     } else {

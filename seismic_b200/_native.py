@@ -138,6 +138,7 @@ SYMBOLS = {
     "shost_synth_documents": (C.c_int, [C.POINTER(SynthConfig), C.POINTER(C.c_void_p)]),
     "shost_synth_queries": (C.c_int, [C.POINTER(SynthConfig), C.c_uint64, C.POINTER(C.c_void_p)]),
     "shost_index_build": (C.c_int, [C.c_void_p, C.POINTER(BuildConfig), C.POINTER(C.c_void_p)]),
+    "shost_index_convert_dotvbyte": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "shost_index_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "shost_index_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "shost_index_destroy": (None, [C.c_void_p]),

@@ -153,6 +153,16 @@ class HostIndex:
     def save(self, path: str) -> None:
         N.check(N.lib().shost_index_save(self._h, str(path).encode()))
 
+    def convert_to_dotvbyte(self) -> "HostIndex":
+        """Same posting lists over a DotVByte forward index (reference src/pylib/dotvbyte.rs:195-213)."""
+        out = C.c_void_p()
+        N.check(N.lib().shost_index_convert_dotvbyte(self._h, C.byref(out)))
+        return HostIndex(out.value)
+
+    @property
+    def value_kind(self) -> int:
+        return int(self._view.value_kind)
+
     @property
     def view(self) -> N.IndexView:
         return self._view
@@ -197,7 +207,8 @@ class HostIndex:
         fo = N.np_view(v.fwd_offsets, n + 1, np.uint64)
         return {
             "fwd_offsets": fo,
-            "fwd_comps": N.np_view(v.fwd_comps, int(fo[-1]), np.uint16 if v.comp_bits == 16 else np.uint32),
+            "fwd_comps": N.np_view(v.fwd_comps, int(fo[-1]) if v.fwd_comps else 0,
+                                   np.uint16 if v.comp_bits == 16 else np.uint32),
             "list_post_start": lps, "postings": N.np_view(v.postings, int(lps[-1]), np.uint64),
             "list_blk_start": lbs, "blk_post_off": N.np_view(v.blk_post_off, int(lbs[-1]) + dim, np.uint32),
             "blk_min": N.np_view(v.blk_min, int(lbs[-1]), np.float32),

@@ -60,6 +60,8 @@ struct DevIndex {
     uint64_t n_docs;
     uint32_t dim;
     uint32_t comp32;  // 1: u32 components (Rec32 records, 16-byte units), 0: u16 components (Rec16, 32-byte units)
+    uint32_t vbyte;   // 1: DotVByte byte stream (4-byte units), u16 components
+    float value_scale;
 };
 
 struct Batch {

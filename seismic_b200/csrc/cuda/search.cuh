@@ -63,6 +63,7 @@ struct SearchArgs {
     uint32_t first_wave_docs;  // soft cap for the first wave of a query (heap still empty)
     uint32_t buf_docs;         // capacity of the wave buffers (>= wave caps); larger blocks are split
     uint32_t qd_words;         // 32-bit words of the query table (meaning depends on the query type)
+    float value_scale;         // DotVByte: value = code * value_scale
     float* out_scores;         // [nq*k] (chunk-relative)
     uint32_t* out_counts;      // [nq]
 };
@@ -100,6 +101,9 @@ struct DenseQuery {
         acc = __fadd_rn(acc, __fmul_rn(qd[cw & 0xffffu], h_lo(vw)));
         return __fadd_rn(acc, __fmul_rn(qd[cw >> 16], h_hi(vw)));
     }
+    __device__ __forceinline__ float mac_f(float acc, uint32_t c, float val) const {
+        return __fadd_rn(acc, __fmul_rn(qd[c], val));
+    }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
         qd = reinterpret_cast<float*>(base);
@@ -134,6 +138,10 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
         acc = __fadd_rn(acc, __fmul_rn(vals[qidx[cw & 0xffffu]], h_lo(vw)));
         return __fadd_rn(acc, __fmul_rn(vals[qidx[cw >> 16]], h_hi(vw)));
 #endif
+    }
+    __device__ __forceinline__ float mac_f(float acc, uint32_t c, float val) const {
+        const uint32_t i = qidx[c];
+        return i ? __fadd_rn(acc, __fmul_rn(vals[i], val)) : acc;
     }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
@@ -336,6 +344,77 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
     }
 }
 
+// ---- DotVByte records: gap-coded u16 components (1 or 2 bytes per gap) + u8 values --------
+// Format: csrc/host/build.cpp (convert_dotvbyte).  The posting's start field counts 4-byte units of the byte
+// stream.  Each chunk of 8 components is self-contained (absolute base), so lane8 decodes chunks lane8, lane8+8, ...
+// exactly like the plain layouts; the chunk's offset in the gap stream is 7*m + popcount(ctrl[0..m)).
+struct RecVB {
+    static constexpr bool VBYTE = true;
+};
+template <class R>
+struct is_vbyte { static constexpr bool value = false; };
+template <>
+struct is_vbyte<RecVB> { static constexpr bool value = true; };
+
+template <int D, class Q>
+__device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream, const uint64_t (&post)[D],
+                                              uint32_t lane8, uint32_t rounds, const Q& q, float scale,
+                                              float (&acc)[D], uint32_t& bytes) {
+    const uint8_t* rec[D];
+    uint32_t nch[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        rec[j] = stream + (post[j] >> 16) * 4;
+        nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
+        acc[j] = 0.f;
+        if (lane8 == 0) bytes += ((2 * nch[j] + 3) & ~3u) + ((nch[j] + 3) & ~3u) + 15 * nch[j];
+    }
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t m = lane8 + 8 * r;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (m >= nch[j]) continue;
+            const uint32_t n = nch[j];
+            const uint8_t* ctrl_p = rec[j] + ((2 * n + 3) & ~3u);
+            const uint8_t* vals_p = ctrl_p + ((n + 3) & ~3u);
+            const uint8_t* gaps_p = vals_p + 8 * n;
+            uint32_t c = __ldg(reinterpret_cast<const uint16_t*>(rec[j]) + m);
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(ctrl_p);
+            uint32_t pc = 0;
+            for (uint32_t w = 0; w < (m >> 2); ++w) pc += __popc(__ldg(cw + w));
+            const uint32_t wlast = __ldg(cw + (m >> 2));
+            pc += __popc(wlast & ((1u << (8 * (m & 3))) - 1u));
+            const uint32_t ctrl = (wlast >> (8 * (m & 3))) & 0xffu;
+            bytes += __popc(ctrl);
+            const uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(vals_p) + 2 * m);
+            const uint32_t v1 = __ldg(reinterpret_cast<const uint32_t*>(vals_p) + 2 * m + 1);
+            // 16-byte window of the gap stream at an arbitrary byte address
+            const uint8_t* g = gaps_p + 7 * m + pc;
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)3);
+            const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(g) & 3u) * 8;
+            const uint32_t w0 = __ldg(gw), w1 = __ldg(gw + 1), w2 = __ldg(gw + 2), w3 = __ldg(gw + 3), w4 = __ldg(gw + 4);
+            uint64_t lo = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+            uint64_t hi = ((uint64_t)__funnelshift_r(w3, w4, sh) << 32) | __funnelshift_r(w2, w3, sh);
+            float a = acc[j];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (e) {
+                    const bool two = (ctrl >> e) & 1u;
+                    c += (uint32_t)lo & (two ? 0xffffu : 0xffu);
+                    const uint32_t s = two ? 16 : 8;
+                    lo = (lo >> s) | (hi << (64 - s));
+                    hi >>= s;
+                }
+                const uint32_t code = ((e < 4 ? v0 : v1) >> (8 * (e & 3))) & 0xffu;
+                // (float)code exactly, without the conversion pipe: 2^23 + code as float bits, minus 2^23
+                const float val = __fmul_rn(__uint_as_float(0x4b000000u | code) - 8388608.f, scale);
+                a = q.mac_f(a, c, val);
+            }
+            acc[j] = a;
+        }
+    }
+}
+
 // ---- bounded top-k kept by ONE warp ------------------------------------------------------------------------
 __device__ __forceinline__ bool better(float s, uint32_t key, float ws, uint32_t wkey) {
     return s > ws || (s == ws && key < wkey);
@@ -509,14 +588,18 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             }
             const uint32_t rounds = (__reduce_max_sync(0xffffffffu, mx) + 63) >> 6;
             float acc[D];
-            score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, acc);
+            if constexpr (is_vbyte<R>::value)
+                score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, a.value_scale,
+                                 acc, st_units);
+            else
+                score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, acc);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const float s = group_reduce(acc[j]);
                 const uint32_t d = dbase + j * GROUPS + grp;
                 if (lane8 == 0 && d < n) {
                     scores[d] = s;
-                    st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
+                    if constexpr (!is_vbyte<R>::value) st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
                     // theta only grows: a document that cannot enter the heap as of the wave start never will
                     if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey))
                         atomicOr(&surv[d >> 5], 1u << (d & 31));

@@ -120,8 +120,11 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
         shost::set_error("sgpu_index_create: null argument");
         return SGPU_EINVAL;
     }
-    if ((v->comp_bits != 16 && v->comp_bits != 32) || v->value_kind != SGPU_VAL_F16) {
-        shost::set_error("sgpu_index_create: this build supports u16/u32 components with f16 values");
+    const bool vbyte = v->value_kind == SGPU_VAL_DOTVBYTE;
+    if ((v->comp_bits != 16 && v->comp_bits != 32) || (v->value_kind != SGPU_VAL_F16 && !vbyte) ||
+        (vbyte && (v->comp_bits != 16 || !v->fwd_nnz))) {
+        shost::set_error("sgpu_index_create: supported forward indexes are u16/u32 components with f16 values and "
+                         "u16 DotVByte");
         return SGPU_EUNSUPPORTED;
     }
     const bool comp32 = v->comp_bits == 32;
@@ -155,7 +158,18 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
 
     // ---- record layout
     std::vector<uint32_t> rec_start(N + 1);
-    {
+    if (vbyte) {  // the packed byte stream is the record buffer; rec_start in 4-byte units
+        const uint64_t bytes = v->fwd_offsets[N];
+        if ((bytes >> 2) >= (1ull << 32)) {
+            shost::set_error("forward index larger than 2^32 record units");
+            return SGPU_EUNSUPPORTED;
+        }
+        for (uint64_t d = 0; d <= N; ++d) rec_start[d] = (uint32_t)(v->fwd_offsets[d] >> 2);
+        CK(ix->fwd.ensure(bytes + 64));
+        CK(cudaMemsetAsync((char*)ix->fwd.p + bytes, 0, 64, st));
+        if (bytes) CK(cudaMemcpyAsync(ix->fwd.p, v->fwd_values, bytes, cudaMemcpyHostToDevice, st));
+        total += bytes;
+    } else {
         uint64_t units = 0;
         for (uint64_t d = 0; d < N; ++d) {
             rec_start[d] = (uint32_t)units;
@@ -177,8 +191,9 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     if (int rc = upload(ix->rec_start, rec_start.data(), N + 1, st, &total)) return rc;
     DevBuf d_fwd_off;
     uint64_t scratch_total = 0;
-    if (int rc = upload(d_fwd_off, v->fwd_offsets, N + 1, st, &scratch_total)) return rc;
-    {
+    if (!vbyte)
+        if (int rc = upload(d_fwd_off, v->fwd_offsets, N + 1, st, &scratch_total)) return rc;
+    if (!vbyte) {
         // pack records on the GPU, ~64 M elements per slice
         const uint64_t slice_elems = 64ull << 20;
         DevBuf d_c, d_v;
@@ -236,7 +251,7 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     ix->max_block_docs = max_block_docs;
     if (int rc = upload(ix->lists, hdr.data(), dim, st, &total)) return rc;
     if (int rc = upload(ix->postings, v->postings, P, st, &total)) return rc;
-    if (P) {
+    if (P && !vbyte) {  // DotVByte postings already carry (byte offset / 4, nnz)
         k_translate_postings<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
             d_fwd_off.as<uint64_t>(), ix->rec_start.as<uint32_t>(), N, ix->postings.as<uint64_t>(), P);
         CK(cudaGetLastError());
@@ -265,6 +280,8 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     d.n_docs = N;
     d.dim = (uint32_t)dim;
     d.comp32 = comp32 ? 1u : 0u;
+    d.vbyte = vbyte ? 1u : 0u;
+    d.value_scale = v->value_scale;
     *out = ix.release();
     return SGPU_OK;
 }
@@ -356,7 +373,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     };
     const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad, DENSE_THREADS);
     const bool comp32 = ix->ix.comp32 != 0;
-    const bool dense_ok = !comp32 && smem_d + 1024 <= ix->smem_optin;
+    const bool vbyte = ix->ix.vbyte != 0;
+    ad.value_scale = ix->ix.value_scale;
+    const bool dense_ok = !comp32 && !vbyte && smem_d + 1024 <= ix->smem_optin;
     typedef void (*kern_t)(const SearchArgs);
     kern_t kd = small_k ? (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, RegHeap>
                         : (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, SmemHeap>;
@@ -367,8 +386,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ah.first_wave_docs = std::max(1u, ix->hq_first_wave_docs);
     ah.buf_docs = std::max(ah.wave_docs, ah.first_wave_docs);
     ah.counter_idx = 3;
-    const int mode = comp32 ? 3 : ix->hq_mode;  // 1 byte index, 2 perfect hash, 3 bitmap + rank (only choice for u32)
-    const bool wide = comp32 || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
+    const int mode = comp32 ? 3 : (vbyte ? 1 : ix->hq_mode);  // 1 byte index, 2 perfect hash, 3 bitmap + rank
+    const bool wide = comp32 || vbyte || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
     const int hq_threads = wide ? 256 : 128;
     size_t qbytes = 0;
     kern_t kh = nullptr;
@@ -380,6 +399,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         ah.qd_words = ((ix->ix.dim + 15u) / 16u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 4;
         kh = SGPU_PICK(ByteQuery, 6, 2);
+        if (vbyte)
+            kh = small_k ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, RecVB>
+                         : (kern_t)k_search<256, 4, 2, ByteQuery, SmemHeap, RecVB>;
     } else if (mode == 2) {
         qbytes = (size_t)HQ_SLOTS * 6;
         kh = SGPU_PICK(HashQuery, 6, 2);
@@ -393,7 +415,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     }
 #undef SGPU_PICK
     const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
-    bool hq_ok = (comp32 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
+    bool hq_ok = (comp32 || vbyte || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
     if (hq_ok) {
         CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
@@ -501,7 +523,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         stats->docs_scored = hs[0];
         stats->blocks_scored = hs[1];
         stats->blocks_pushed = hs[2];
-        stats->fwd_bytes = hs[3] * (ix->ix.comp32 ? 48ull : 32ull);
+        stats->fwd_bytes = hs[3] * (ix->ix.vbyte ? 1ull : (ix->ix.comp32 ? 48ull : 32ull));
     }
     return SGPU_OK;
 }
@@ -621,8 +643,8 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
         shost::set_error("sgpu_exact_search: bad argument");
         return SGPU_EINVAL;
     }
-    if (ix->ix.comp32) {
-        shost::set_error("sgpu_exact_search: not available for u32-component indexes");
+    if (ix->ix.comp32 || ix->ix.vbyte) {
+        shost::set_error("sgpu_exact_search: only available for u16/f16 indexes");
         return SGPU_EUNSUPPORTED;
     }
     CK(cudaSetDevice(ix->device));

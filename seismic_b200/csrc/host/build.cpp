@@ -717,3 +717,116 @@ void fill_view(const ShostIndex& idx, SgpuIndexView* v) {
 }
 
 }  // namespace shost
+
+// ---------------------------------------------------------------------------------------------------------
+// DotVByte conversion.  The reference builds a standard u16/f16 index and then converts the
+// forward index to `PackedSparseDataset<DotVByteFixedU8Encoder>` (src/pylib/dotvbyte.rs:195-213), re-packing the
+// postings to the packed storage's ranges (src/inverted_index.rs:237-275).  The byte format of that encoder lives
+// in the absent `vectorium` crate, so this is OUR documented format (not byte-compatible):
+//
+//   value    u8 code, value = code * scale, scale = (largest f16 value of the collection) / 255   (FixedU8)
+//   record   4-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)):
+//              base  u16[nch]   absolute first component of each chunk          (padded to 4 bytes)
+//              ctrl  u8[nch]    bit j (1..7): gap j of the chunk takes 2 bytes   (padded to 4 bytes)
+//              vals  u8[8*nch]  codes, tail padded with 0
+//              gaps  per chunk 7 gaps c_j - c_{j-1}, 1 or 2 bytes little endian (variable byte), tail gaps 0
+//   fwd_offsets[i]  byte offset of record i;  fwd_nnz[i] number of components;  postings = (offset/4 << 16) | nnz
+// A chunk is self-contained (absolute base), so the 8 lanes of a GPU group decode 8 chunks in parallel; the offset
+// of chunk m in the gap stream is 7*m + popcount(ctrl[0..m)).
+namespace shost {
+
+static inline uint32_t vb_header_bytes(uint32_t nch) { return ((2 * nch + 3) & ~3u) + ((nch + 3) & ~3u) + 8 * nch; }
+
+int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
+    if (in.comp_bits != 16 || in.value_kind != SGPU_VAL_F16) {
+        set_error("DotVByte conversion needs a u16/f16 index");
+        return SGPU_EUNSUPPORTED;
+    }
+    const uint64_t N = in.n_docs;
+    const uint64_t* off = in.sec[SEC_FWD_OFFSETS].as<uint64_t>();
+    const uint16_t* comps = in.sec[SEC_FWD_COMPS].as<uint16_t>();
+    const uint16_t* vals = in.sec[SEC_FWD_VALUES].as<uint16_t>();
+    const unsigned T = hw_threads(in.config.n_threads);
+    float mx = 0.f;
+    for (uint64_t i = 0; i < in.nnz; ++i) mx = std::max(mx, f16_bits_to_f32(vals[i]));
+    const float scale = mx > 0.f ? mx / 255.f : 1.f;
+    // pass 1: record sizes
+    std::vector<uint64_t> boff(N + 1, 0);
+    parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t d = b; d < e; ++d) {
+            const uint64_t s = off[d], n = off[d + 1] - s;
+            const uint32_t nch = (uint32_t)((n + 7) >> 3);
+            uint64_t bytes = vb_header_bytes(nch);
+            for (uint32_t m = 0; m < nch; ++m)
+                for (uint32_t j = 1; j < 8; ++j) {
+                    const uint64_t i = (uint64_t)m * 8 + j;
+                    const uint32_t gap = i < n ? (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1] : 0u;
+                    bytes += gap < 256 ? 1 : 2;
+                }
+            boff[d + 1] = (bytes + 3) & ~3ull;
+        }
+    });
+    for (uint64_t d = 0; d < N; ++d) boff[d + 1] += boff[d];
+    if ((boff[N] >> 2) >= (1ull << 48)) { set_error("packed forward index too large"); return SGPU_EUNSUPPORTED; }
+    auto* idx = new ShostIndex();
+    idx->comp_bits = 16;
+    idx->value_kind = SGPU_VAL_DOTVBYTE;
+    idx->n_docs = N;
+    idx->dim = in.dim;
+    idx->nnz = in.nnz;
+    idx->value_scale = scale;
+    idx->config = in.config;
+    idx->sec[SEC_FWD_OFFSETS].adopt(boff);
+    uint8_t* stream = idx->sec[SEC_FWD_VALUES].alloc<uint8_t>(boff[N] + 32);  // 32 bytes of slack for wide loads
+    uint16_t* nnzs = idx->sec[SEC_FWD_NNZ].alloc<uint16_t>(N);
+    parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t d = b; d < e; ++d) {
+            const uint64_t s = off[d], n = off[d + 1] - s;
+            const uint32_t nch = (uint32_t)((n + 7) >> 3);
+            nnzs[d] = (uint16_t)n;
+            uint8_t* rec = stream + boff[d];
+            uint16_t* base = (uint16_t*)rec;
+            uint8_t* ctrl = rec + ((2 * nch + 3) & ~3u);
+            uint8_t* vv = ctrl + ((nch + 3) & ~3u);
+            uint8_t* gp = vv + 8 * nch;
+            for (uint32_t m = 0; m < nch; ++m) {
+                base[m] = comps[s + (uint64_t)m * 8];
+                uint8_t c = 0;
+                for (uint32_t j = 0; j < 8; ++j) {
+                    const uint64_t i = (uint64_t)m * 8 + j;
+                    float r = i < n ? std::nearbyint(f16_bits_to_f32(vals[s + i]) / scale) : 0.f;
+                    vv[m * 8 + j] = (uint8_t)std::min(255.f, std::max(0.f, r));
+                    if (j == 0) continue;
+                    const uint32_t gap = i < n ? (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1] : 0u;
+                    *gp++ = (uint8_t)(gap & 0xff);
+                    if (gap >= 256) {
+                        *gp++ = (uint8_t)(gap >> 8);
+                        c |= (uint8_t)(1u << j);
+                    }
+                }
+                ctrl[m] = c;
+            }
+        }
+    });
+    // posting lists: same blocks and summaries; postings re-packed to (byte offset / 4, nnz)
+    for (int sidx : {SEC_LIST_POST_START, SEC_LIST_BLK_START, SEC_BLK_POST_OFF, SEC_BLK_MIN, SEC_BLK_QUANT,
+                     SEC_LIST_SC_START, SEC_SC_COMP, SEC_LIST_ENT_START, SEC_SC_RUN_OFF, SEC_ENT_BLK, SEC_ENT_CODE}) {
+        idx->sec[sidx].own.assign(in.sec[sidx].ptr, in.sec[sidx].ptr + in.sec[sidx].bytes);
+        idx->sec[sidx].ptr = idx->sec[sidx].own.data();
+        idx->sec[sidx].bytes = in.sec[sidx].bytes;
+    }
+    const uint64_t P = in.sec[SEC_POSTINGS].count<uint64_t>();
+    const uint64_t* pin = in.sec[SEC_POSTINGS].as<uint64_t>();
+    uint64_t* pout = idx->sec[SEC_POSTINGS].alloc<uint64_t>(P);
+    parallel_for(P, 1 << 16, T, [&](uint64_t b, uint64_t e, unsigned) {
+        for (uint64_t i = b; i < e; ++i) {
+            const uint64_t start = pin[i] >> 16;
+            const uint64_t d = (uint64_t)(std::upper_bound(off, off + N + 1, start) - off) - 1;
+            pout[i] = ((boff[d] >> 2) << 16) | (pin[i] & 0xffff);
+        }
+    });
+    *out = idx;
+    return SGPU_OK;
+}
+
+}  // namespace shost

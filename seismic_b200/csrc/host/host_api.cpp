@@ -91,6 +91,13 @@ int shost_index_build(const ShostDataset* ds, const ShostBuildConfig* cfg, Shost
         return SGPU_EINVAL;
     }
 }
+int shost_index_convert_dotvbyte(const ShostIndex* idx, ShostIndex** out) {
+    if (!idx || !out) {
+        set_error("shost_index_convert_dotvbyte: null argument");
+        return SGPU_EINVAL;
+    }
+    return convert_dotvbyte(*idx, out);
+}
 int shost_index_save(const ShostIndex* idx, const char* path) { return save_index(*idx, path); }
 int shost_index_load(const char* path, ShostIndex** out) { return load_index(path, out); }
 void shost_index_destroy(ShostIndex* idx) { delete idx; }

@@ -71,6 +71,7 @@ struct ShostIndex {
 
 namespace shost {
 int build_index(const ShostDataset& ds, const ShostBuildConfig& cfg, ShostIndex** out);
+int convert_dotvbyte(const ShostIndex& in, ShostIndex** out);
 int save_index(const ShostIndex& idx, const char* path);
 int load_index(const char* path, ShostIndex** out);
 void fill_view(const ShostIndex& idx, SgpuIndexView* v);

@@ -127,6 +127,43 @@ def test_large_vocabulary_query_limit(synth_lv):
     assert counts[0] <= 10
 
 
+@pytest.mark.parametrize("k,cut,hf,srt", [(10, 3, 0.8, True), (10, 3, 0.8, False), (100, 6, 0.9, True)])
+def test_parity_dotvbyte(oracle_mod, synth_pruned, k, cut, hf, srt):
+    """SeismicIndexDotVByte: variable-byte gaps + u8 values decoded inside the scoring kernel."""
+    _, q, index = synth_pruned
+    vb = index.convert_to_dotvbyte()
+    assert vb.value_kind == N.VAL_DOTVBYTE and vb.space_usage()["forward"] < 0.7 * index.space_usage()["forward"]
+    g = GpuIndex(vb, 0)
+    ref = oracle_mod.batch_search(vb.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    assert_same(got, ref, f"dotvbyte k={k} cut={cut} hf={hf} sorted={srt}")
+    assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+    # the u8 re-quantisation keeps the ranking close to the f16 index it was converted from
+    ref16 = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    assert recall_at_k(ref16[0], ref16[2], got[0], got[2]) > 0.9
+
+
+def test_dotvbyte_wide_documents(oracle_mod):
+    """Documents with hundreds of components (many chunks: the prefix popcount spans several control words) and
+    gaps that straddle every byte alignment."""
+    rng = np.random.default_rng(5)
+    comps, vals = [], []
+    for i in range(600):
+        n = int(rng.integers(1, 700))
+        comps.append(np.sort(rng.choice(60000, size=n, replace=False)).astype(np.uint32))
+        vals.append((rng.random(n, dtype=np.float32) * 3 + 0.01).astype(np.float32))
+    comps.append(np.empty(0, np.uint32)); vals.append(np.empty(0, np.float32))        # an empty document
+    index = HostIndex.build(Dataset.from_lists(comps, vals, dim=60000), n_postings=50)
+    vb = index.convert_to_dotvbyte()
+    g = GpuIndex(vb, 0)
+    qc = [np.sort(rng.choice(60000, size=200, replace=False)).astype(np.uint32) for _ in range(40)] + [comps[3][:250], comps[77][:250]]   # compact queries hold <= 255 components
+    qv = [rng.random(len(c), dtype=np.float32) for c in qc]
+    off = np.zeros(len(qc) + 1, np.uint64); off[1:] = np.cumsum([len(c) for c in qc])
+    ref = oracle_mod.batch_search(vb.view, off, np.concatenate(qc), np.concatenate(qv), 10, 20, 0.0, first_sorted=False)
+    got = g.batch_search(off, np.concatenate(qc), np.concatenate(qv), 10, 20, 0.0, first_sorted=False)
+    assert_same(got, ref, "dotvbyte wide docs")
+
+
 def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
     _, q, index = synth_small
     g = GpuIndex(index, 0)
