@@ -381,11 +381,16 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
             for (uint64_t i = p0; i < p1; ++i) {  // prefetch pass (src/posting_list.rs:198-204)
                 uint64_t start = posts[i] >> 16;
                 if (cx.visited.contains(start)) continue;
+                // prefetch_with_range: every cache line of the vector's components and values
+                const uint32_t plen = (uint32_t)(posts[i] & 0xffff);
                 if (vbyte) {
-                    __builtin_prefetch((const uint8_t*)v.fwd_values + start * 4);
+                    const uint8_t* pr = (const uint8_t*)v.fwd_values + start * 4;
+                    for (uint32_t x = 0; x < plen * 5 / 2 + 64; x += 64) __builtin_prefetch(pr + x);
                 } else {
-                    __builtin_prefetch((const uint8_t*)v.fwd_comps + start * cbytes);
-                    __builtin_prefetch((const uint8_t*)v.fwd_values + start * vbytes);
+                    const uint8_t* pc = (const uint8_t*)v.fwd_comps + start * cbytes;
+                    const uint8_t* pv = (const uint8_t*)v.fwd_values + start * vbytes;
+                    for (uint32_t x = 0; x < plen * cbytes; x += 64) __builtin_prefetch(pc + x);
+                    for (uint32_t x = 0; x < plen * vbytes; x += 64) __builtin_prefetch(pv + x);
                 }
             }
             for (uint64_t i = p0; i < p1; ++i) {

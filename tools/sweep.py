@@ -15,23 +15,36 @@ ap.add_argument("--centroid-fraction", type=float, default=0.1)
 ap.add_argument("--summary-energy", type=float, default=0.4)
 ap.add_argument("--max-fraction", type=float, default=1.5)
 ap.add_argument("--k", type=int, default=10)
+ap.add_argument("--dim", type=int, default=30522)
+ap.add_argument("--comp-bits", type=int, default=16)
+ap.add_argument("--doc-nnz-mean", type=float, default=115.0)
+ap.add_argument("--sorted", type=int, default=1)
+ap.add_argument("--dotvbyte", action="store_true", help="also time the DotVByte conversion of the same index")
+ap.add_argument("--cuts", default="3,4,5,6,8,10")
+ap.add_argument("--hfs", default="0.8,0.9,1.0")
 a = ap.parse_args()
-cfg = Dataset.synth_config(a.docs)
+cfg = Dataset.synth_config(a.docs, dim=a.dim, doc_nnz_mean=a.doc_nnz_mean)
 t = time.time(); docs = Dataset.synth_documents(cfg); print("gen", round(time.time() - t, 1), flush=True)
 t = time.time(); index = HostIndex.build(docs, n_postings=a.n_postings, centroid_fraction=a.centroid_fraction,
-                                         summary_energy=a.summary_energy, max_fraction=a.max_fraction)
+                                         summary_energy=a.summary_energy, max_fraction=a.max_fraction, comp_bits=a.comp_bits)
 print("build", round(time.time() - t, 1), index.space_usage(), flush=True)
 del docs
 q = Dataset.synth_queries(cfg, a.queries)
 gpu = GpuIndex(index, 0)
 nr = min(a.recall_queries, a.queries)
 r_off = q.offsets[: nr + 1]
-ex = gpu.exact_search(r_off, q.comps[: int(r_off[-1])], q.values[: int(r_off[-1])], a.k)
-print("exact ms", gpu.last_stats, flush=True)
+if a.comp_bits == 16:
+    ex = gpu.exact_search(r_off, q.comps[: int(r_off[-1])], q.values[: int(r_off[-1])], a.k)
+    print("exact ms", gpu.last_stats, flush=True)
+else:  # no GPU exact kernel for u32 components: CPU brute force on the sample
+    import oracle
+    t = time.time()
+    ex = oracle.exact_search(index.view, r_off, q.comps[: int(r_off[-1])], q.values[: int(r_off[-1])], a.k)
+    print("exact (cpu) s", round(time.time() - t, 1), flush=True)
 rows = []
-for cut in (3, 4, 5, 6, 8, 10):
-    for hf in (0.8, 0.9, 1.0):
-        for srt in (True,):
+for cut in [int(x) for x in a.cuts.split(',')]:
+    for hf in [float(x) for x in a.hfs.split(',')]:
+        for srt in (bool(a.sorted),):
             best = None
             for rep in range(3):
                 ids, sc, cnt = gpu.batch_search(q.offsets, q.comps, q.values, a.k, cut, hf, first_sorted=srt)
@@ -39,6 +52,17 @@ for cut in (3, 4, 5, 6, 8, 10):
                 if best is None or st["ms_total"] < best["ms_total"]:
                     best = st
             rec = recall_at_k(ex[0], ex[2], ids[:nr], cnt[:nr])
+            if a.comp_bits == 32 and cut == int(a.cuts.split(',')[0]) and hf == float(a.hfs.split(',')[0]):
+                import oracle
+                n = min(2000, a.queries)
+                o = q.offsets[: n + 1]
+                ref = oracle.batch_search(index.view, o, q.comps[: int(o[-1])], q.values[: int(o[-1])], a.k, cut, hf,
+                                          first_sorted=srt, n_threads=0)
+                print(json.dumps({"lv_parity_mismatch_first_%d" % n: int(((ids[:n] != ref[0]).any(axis=1) | (cnt[:n] != ref[2])).sum()),
+                                  "scores_equal": bool(np.array_equal(sc[:n], ref[1])),
+                                  "cpu_all_threads_qps": round(n / ref[3]["seconds"]),
+                                  "algorithmic_bytes_per_query": ref[3]["bytes_total"] / n,
+                                  "image_GB": round(gpu.device_bytes / 1e9, 2)}), flush=True)
             row = {"query_cut": cut, "heap_factor": hf, "sorted": srt, "recall": round(rec, 4),
                    "qps_kernels": round(a.queries / best["ms_total"] * 1e3), "ms_search": round(best["ms_search"], 3),
                    "ms_total": round(best["ms_total"], 3), "docs_per_query": round(best["docs_scored"] / a.queries, 1)}
@@ -46,3 +70,30 @@ for cut in (3, 4, 5, 6, 8, 10):
             print(json.dumps(row), flush=True)
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/sweep_%d.json" % a.docs).write_text(json.dumps(rows, indent=1))
+
+if a.dotvbyte:
+    import oracle
+    t = time.time(); vb = index.convert_to_dotvbyte(); print("dotvbyte convert", round(time.time() - t, 1), vb.space_usage(), flush=True)
+    del gpu
+    g = GpuIndex(vb, 0)
+    for cut, hf in ((3, 0.8),):
+        best = None
+        for rep in range(4):
+            ids, sc, cnt = g.batch_search(q.offsets, q.comps, q.values, a.k, cut, hf, first_sorted=True)
+            st = dict(g.last_stats)
+            if best is None or st["ms_total"] < best["ms_total"]:
+                best = st
+        n = min(2000, a.queries)
+        o = q.offsets[: n + 1]
+        ref = oracle.batch_search(vb.view, o, q.comps[: int(o[-1])], q.values[: int(o[-1])], a.k, cut, hf, first_sorted=True, n_threads=0)
+        mism = int(((ids[:n] != ref[0]).any(axis=1) | (cnt[:n] != ref[2])).sum())
+        rec = recall_at_k(ex[0], ex[2], ids[:nr], cnt[:nr])
+        all_ref = oracle.batch_search(vb.view, q.offsets, q.comps, q.values, a.k, cut, hf, first_sorted=True, n_threads=0)
+        alg = all_ref[3]["bytes_postings"] + all_ref[3]["bytes_forward"] + all_ref[3]["bytes_query_out"]
+        row = {"dotvbyte": True, "query_cut": cut, "heap_factor": hf, "recall_vs_f16_exact": round(rec, 4),
+               "qps_kernels": round(a.queries / best["ms_total"] * 1e3), "ms_search": round(best["ms_search"], 3),
+               "parity_mismatch_first_2000": mism, "scores_equal": bool(np.array_equal(sc[:n], ref[1])),
+               "algorithmic_GBps_k_search": round(alg / best["ms_search"] / 1e6, 1), "fwd_bytes_read": best["fwd_bytes"],
+               "cpu_all_threads_qps": round(a.queries / all_ref[3]["seconds"]), "image_GB": round(g.device_bytes / 1e9, 2)}
+        print(json.dumps(row), flush=True)
+        Path("gpurun_out/sweep_dotvbyte_%d.json" % a.docs).write_text(json.dumps(row, indent=1))
