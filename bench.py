@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=2000, help="queries of the CPU baseline sample")
     ap.add_argument("--wave-docs", type=int, default=0)
     ap.add_argument("--first-wave-docs", type=int, default=0)
+    ap.add_argument("--r97-cut", type=int, default=5, help="query_cut of the extra run that reaches recall@10 >= 0.97")
+    ap.add_argument("--r97-hf", type=float, default=0.9)
     ap.add_argument("--keep-index", action="store_true")
     return ap.parse_args()
 
@@ -335,6 +337,24 @@ def main():
             r_off = q_off[: nr + 1]
             ex = gpu.exact_search(r_off, q_c[: int(r_off[-1])], q_v[: int(r_off[-1])], k)
             recall = recall_at_k(ex[0], ex[2], ids[:nr], counts[:nr])
+        # BASELINE's metric is "queries/sec at recall@10 >= 0.97": the named config (query_cut=3, heap_factor=0.8) is
+        # not a tuned point of the reference and reaches ~0.95 on this corpus, so the nearest config
+        # that does reach 0.97 is measured too (same batch, device-resident inputs, CUDA events of the library).
+        r97 = None
+        if a.recall_queries > 0 and a.r97_cut > 0:
+            ms = []
+            for i in range(3 + min(a.steps, 20)):
+                st97 = gpu.batch_search_device(d_off.data_ptr(), d_c.data_ptr(), d_v.data_ptr(), nq, k, a.r97_cut,
+                                               a.r97_hf, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                                               first_sorted=bool(a.sorted))
+                if i >= 3:
+                    ms.append(st97["ms_total"])
+            torch.cuda.synchronize()
+            ids97 = d_ids.cpu().numpy().view(np.uint64)
+            cnt97 = d_cnt.cpu().numpy().view(np.uint32)
+            r97 = {"query_cut": a.r97_cut, "heap_factor": a.r97_hf, "recall_at_k": recall_at_k(ex[0], ex[2], ids97[:nr], cnt97[:nr]),
+                   "value": world * nq / (float(np.mean(ms)) * 1e-3), "unit": "queries/s (sum of kernel times, per-GPU x n_gpus)",
+                   "ms_per_step": float(np.mean(ms))}
         ms_search = float(np.mean([s["ms_search"] for s in stats]))
         ms_kernels = float(np.mean([s["ms_total"] for s in stats]))
         alg_search = ost["bytes_postings"] + ost["bytes_forward"] + ost["bytes_query_out"]
@@ -373,6 +393,7 @@ def main():
             "parity": {"queries": nq, "id_mismatch_queries_host_api": mism, "id_mismatch_queries_device_api": mism_dev,
                        "scores_bit_identical": score_ok},
             "recall_at_k": recall,
+            "at_recall_0.97": r97,
             "kernel_ms": {k2: float(np.mean([s[k2] for s in stats])) for k2 in
                           ("ms_prep", "ms_summary", "ms_search", "ms_finish", "ms_total")},
             "work": {"docs_scored_gpu": int(stats[-1]["docs_scored"]), "docs_scored_reference": int(ost["docs_scored"]),

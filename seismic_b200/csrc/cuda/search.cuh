@@ -745,27 +745,30 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 // ---------------- phase 3: score the wave
                 score_wave(n_docs);
                 __syncthreads();
+                // best surviving score of every candidate block (cand_p0 is free again: reuse it as cand_max)
+                float* cand_max = reinterpret_cast<float*>(cand_p0);
+                for (uint32_t j = tid; j < n_cand; j += T) {
+                    float mx = -INFINITY;
+                    for (uint32_t i = j ? cand_end[j - 1] : 0u; i < cand_end[j]; ++i)
+                        if ((surv[i >> 5] >> (i & 31)) & 1u) mx = fmaxf(mx, scores[i]);
+                    cand_max[j] = mx;
+                }
+                __syncthreads();
                 lap(3);
                 // ---------------- phase 4: exact replay by warp 0
                 if (warp == 0) {
                     st_docs += n_docs;
                     st_blocks += n_cand;
-                    // 32 candidate blocks at a time: blocks without survivors only need the skip test (counted,
-                    // heap untouched); the first block WITH survivors that passes the test against the live theta
-                    // is pushed, which may raise theta, so the scan restarts right after it.
+                    // 32 candidate blocks at a time: a block whose best surviving score cannot enter the live heap
+                    // only needs the skip test (counted, heap untouched); the first block that can AND passes the
+                    // test against the live theta is pushed, which may raise theta, so the scan restarts after it.
                     uint32_t j0 = 0;
                     while (j0 < n_cand) {
                         const uint32_t j = j0 + lane;
                         const bool valid = j < n_cand;
                         const uint32_t s0 = valid && j ? cand_end[j - 1] : 0u, s1 = valid ? cand_end[j] : 0u;
-                        bool has = false;
-                        if (valid)
-                            for (uint32_t w = s0 >> 5; w <= (s1 - 1) >> 5; ++w) {
-                                uint32_t bits = surv[w];
-                                if (w == (s0 >> 5)) bits &= 0xffffffffu << (s0 & 31);
-                                if (w == ((s1 - 1) >> 5)) bits &= 0xffffffffu >> (31 - ((s1 - 1) & 31));
-                                has |= bits != 0;
-                            }
+                        const float mx = valid ? cand_max[j] : -INFINITY;
+                        const bool has = mx > -INFINITY && (!heap.full() || mx >= heap.theta);
                         const bool passes =
                             valid && !(heap.full() && cand_est[j] < __fmul_rn(a.heap_factor, heap.theta));
                         const uint32_t pm = __ballot_sync(0xffffffffu, passes);
