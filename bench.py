@@ -365,6 +365,14 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_search / (ms_search * 1e-3) / 1e9
+        traffic = None  # per-launch DRAM bytes of k_search from the committed ncu capture of this exact workload
+        try:
+            tr = json.loads((REPO / "profiles" / "r1_traffic.json").read_text())
+            if (tr["docs"], tr["queries"], tr["k"], tr["query_cut"], tr["sorted"]) == (a.docs, nq, k, a.query_cut, a.sorted) \
+                    and abs(tr["heap_factor"] - a.heap_factor) < 1e-6:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         qps = world * nq * a.steps / (dev_ms * 1e-3)
         e2e_qps = world * nq * len(e2e_times) / (e2e_ms * 1e-3)
         out = {
@@ -381,7 +389,7 @@ def main():
                     "d2h_bytes_per_step": int(ids.nbytes + scores.nbytes + counts.nbytes)},
             "gpu_launches": int(sum(s["n_launches"] for s in stats)),
             "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (profiling recipe)",
                          "algorithmic_bytes_per_launch": int(alg_search), "ms_per_launch": ms_search,
                          "read_bytes_per_launch": int(stats[-1]["fwd_bytes"])},
