@@ -95,6 +95,7 @@ __device__ __forceinline__ float h_hi(uint32_t vw) { return __high2float(*reinte
 // mac2(acc, cw, vw): acc += q[c_lo]*v_lo ; acc += q[c_hi]*v_hi for the two (u16 component, f16 value) pairs
 // packed in cw / vw, in that order, mul then add.
 struct DenseQuery {
+    static constexpr bool HAS_DOT8 = false;
     float* qd;
     static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return (size_t)a.qd_words * 4; }
     __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
@@ -124,8 +125,42 @@ struct DenseQuery {
 };
 
 struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); vals[0] = +0.0
+    static constexpr bool HAS_DOT8 = true;
     uint8_t* qidx;
     float* vals;
+    uint32_t qidx_s, vals_s;  // the same two arrays as 32-bit shared-memory addresses
+    // One chunk (8 components): the 8 index loads are issued back to back, then the 8 value loads, then the
+    // arithmetic — a warp issues in order, so interleaving "load, test, load, multiply" per component (what the
+    // compiler emits for mac2 under the 64-register budget) exposes the shared-memory latency 16 times per chunk.
+    // Components that are not in the query read vals[0] = +0.0 and add q*v = +0.0: acc is unchanged bit for bit.
+    __device__ __forceinline__ float dot8(float acc, const uint4 c, const uint4 v) const {
+        uint32_t i0, i1, i2, i3, i4, i5, i6, i7;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i0) : "r"(qidx_s + (c.x & 0xffffu)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i1) : "r"(qidx_s + (c.x >> 16)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i2) : "r"(qidx_s + (c.y & 0xffffu)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i3) : "r"(qidx_s + (c.y >> 16)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i4) : "r"(qidx_s + (c.z & 0xffffu)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i5) : "r"(qidx_s + (c.z >> 16)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i6) : "r"(qidx_s + (c.w & 0xffffu)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(i7) : "r"(qidx_s + (c.w >> 16)));
+        float q0, q1, q2, q3, q4, q5, q6, q7;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q0) : "r"(vals_s + i0 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q1) : "r"(vals_s + i1 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q2) : "r"(vals_s + i2 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q3) : "r"(vals_s + i3 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q4) : "r"(vals_s + i4 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q5) : "r"(vals_s + i5 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q6) : "r"(vals_s + i6 * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q7) : "r"(vals_s + i7 * 4));
+        acc = __fadd_rn(acc, __fmul_rn(q0, h_lo(v.x)));
+        acc = __fadd_rn(acc, __fmul_rn(q1, h_hi(v.x)));
+        acc = __fadd_rn(acc, __fmul_rn(q2, h_lo(v.y)));
+        acc = __fadd_rn(acc, __fmul_rn(q3, h_hi(v.y)));
+        acc = __fadd_rn(acc, __fmul_rn(q4, h_lo(v.z)));
+        acc = __fadd_rn(acc, __fmul_rn(q5, h_hi(v.z)));
+        acc = __fadd_rn(acc, __fmul_rn(q6, h_lo(v.w)));
+        return __fadd_rn(acc, __fmul_rn(q7, h_hi(v.w)));
+    }
     static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return 1024 + (size_t)a.qd_words * 4; }
     __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
 #if SGPU_SKIP_MISS
@@ -147,6 +182,8 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
         vals = reinterpret_cast<float*>(base);
         qidx = base + 1024;
+        vals_s = (uint32_t)__cvta_generic_to_shared(vals);
+        qidx_s = (uint32_t)__cvta_generic_to_shared(qidx);
         for (uint32_t i = tid; i < 256; i += T) vals[i] = 0.f;
         uint32_t* w = reinterpret_cast<uint32_t*>(qidx);
         for (uint32_t i = tid; i < a.qd_words; i += T) w[i] = 0u;
@@ -169,6 +206,7 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
 };
 
 struct HashQuery {
+    static constexpr bool HAS_DOT8 = false;
     uint16_t* tags;
     float* vals;
     uint32_t mult;
@@ -215,6 +253,7 @@ struct HashQuery {
 // bm: one bit per vocabulary entry; pre[w]: rank (among the query's distinct components) of the first component
 // of bitmap word w, valid for words that have a bit set; vals[rank].  <= 255 distinct components.
 struct RankQuery {
+    static constexpr bool HAS_DOT8 = false;
     uint32_t* bm;
     uint8_t* pre;
     float* vals;
@@ -273,10 +312,14 @@ struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x 
     static __device__ __forceinline__ void load(const uint4* p, Chunk& k) { ld_chunk(p, k.c, k.v); }
     template <class Q>
     static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q) {
-        acc = q.mac2(acc, k.c.x, k.v.x);
-        acc = q.mac2(acc, k.c.y, k.v.y);
-        acc = q.mac2(acc, k.c.z, k.v.z);
-        return q.mac2(acc, k.c.w, k.v.w);
+        if constexpr (Q::HAS_DOT8) {
+            return q.dot8(acc, k.c, k.v);
+        } else {
+            acc = q.mac2(acc, k.c.x, k.v.x);
+            acc = q.mac2(acc, k.c.y, k.v.y);
+            acc = q.mac2(acc, k.c.z, k.v.z);
+            return q.mac2(acc, k.c.w, k.v.w);
+        }
     }
 };
 struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16] = 48 bytes = 3 x uint4, unit 16 bytes

@@ -91,6 +91,7 @@ struct SgpuIndex {
     int hq_enabled = 1, hq_ctas_per_sm = 0;
     int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
     int hq_threads = 256;
+    int hq_occ = 4;   // CTAs per SM the 256-thread compact kernel is compiled for (4: 64 registers, 3: 80 registers)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
     // per-batch scratch (grow-only)
@@ -392,7 +393,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     size_t qbytes = 0;
     kern_t kh = nullptr;
 #define SGPU_PICK(Q, OCC128, D128)                                                                        \
-    (wide ? (small_k ? (kern_t)k_search<256, 4, 2, Q, RegHeap> : (kern_t)k_search<256, 4, 2, Q, SmemHeap>) \
+    (wide ? (small_k ? (ix->hq_occ == 3 ? (kern_t)k_search<256, 3, 2, Q, RegHeap> : (kern_t)k_search<256, 4, 2, Q, RegHeap>) \
+                     : (kern_t)k_search<256, 4, 2, Q, SmemHeap>)                                          \
           : (small_k ? (kern_t)k_search<128, OCC128, D128, Q, RegHeap>                                     \
                      : (kern_t)k_search<128, OCC128, D128, Q, SmemHeap>))
     if (mode == 1) {
@@ -564,6 +566,7 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
         return SGPU_EINVAL;
     }
     if (n == "hq_threads") ix->hq_threads = (int)value;
+    else if (n == "hq_occ") ix->hq_occ = (int)value;
     else if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
     else if (n == "hq_first_wave_docs") ix->hq_first_wave_docs = (uint32_t)value;
     else if (n == "hq_ctas_per_sm") ix->hq_ctas_per_sm = (int)value;
