@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
             r0 = __ldg(a.rec_start + d);
             nch = __ldg(a.rec_start + d + 1) - r0;
         }
-        float s = group_reduce(score_rec<Rec16>(a.fwd + (uint64_t)r0 * 2, nch, lane8, dq));
+        float s = group_reduce(score_rec<Rec16>(reinterpret_cast<const char*>(a.fwd) + (uint64_t)r0 * 32, nch, lane8, dq, 1.f));
         if (lane8 == 0 && nch > 0 && (!s_full || better(s, r0, s_theta, s_wkey))) {
             const uint32_t slot = atomicAdd(&s_ncand, 1u);
             cand_s[slot] = s;

@@ -61,6 +61,7 @@ struct DevIndex {
     uint32_t dim;
     uint32_t comp32;  // 1: u32 components (Rec32 records, 16-byte units), 0: u16 components (Rec16, 32-byte units)
     uint32_t vbyte;   // 1: DotVByte byte stream (4-byte units), u16 components
+    uint32_t value_kind;  // SGPU_VAL_* of the records
     float value_scale;
 };
 
@@ -401,6 +402,27 @@ __global__ void k_pack_records32(const uint64_t* fwd_off, const uint32_t* comps,
         const bool ok = i < len;
         rec[ch * 12 + j] = ok ? comps[e0 - elem0 + i] : 0u;
         reinterpret_cast<uint16_t*>(rec + ch * 12 + 8)[j] = ok ? vals[e0 - elem0 + i] : (uint16_t)0;
+    }
+}
+
+// any plain layout: chunk = 8 components (comp_bytes each) followed by 8 values (val_bytes each); rec_start counts
+// unit_bytes units.  Byte-wise, one warp per document (runs once per index).
+__global__ void k_pack_records_any(const uint64_t* fwd_off, const uint8_t* comps, const uint8_t* vals,
+                                   const uint32_t* rec_start, uint64_t doc0, uint64_t n_docs_chunk, uint64_t elem0,
+                                   uint8_t* records, uint32_t comp_bytes, uint32_t val_bytes, uint32_t unit_bytes) {
+    const uint64_t d = doc0 + (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (d >= doc0 + n_docs_chunk) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t e0 = fwd_off[d], len = fwd_off[d + 1] - e0;
+    const uint32_t nch = (uint32_t)((len + 7) >> 3), chunk = 8 * (comp_bytes + val_bytes);
+    uint8_t* rec = records + (uint64_t)rec_start[d] * unit_bytes;
+    for (uint32_t i = lane; i < nch * 8; i += 32) {
+        const uint32_t ch = i >> 3, j = i & 7;
+        const bool ok = i < len;
+        const uint64_t e = e0 - elem0 + i;
+        for (uint32_t b = 0; b < comp_bytes; ++b) rec[ch * chunk + j * comp_bytes + b] = ok ? comps[e * comp_bytes + b] : 0;
+        for (uint32_t b = 0; b < val_bytes; ++b)
+            rec[ch * chunk + 8 * comp_bytes + j * val_bytes + b] = ok ? vals[e * val_bytes + b] : 0;
     }
 }
 

@@ -306,12 +306,14 @@ struct RankQuery {
 // ---- forward-index record layouts ---------------------------------------------------------------------------
 // A record is a sequence of chunks of 8 (component, value) pairs; the posting's start field counts UNIT-byte units.
 struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x uint4, unit 32 bytes
-    static constexpr int U = 2;          // uint4 per chunk
-    static constexpr int START_MUL = 2;  // uint4 per unit of the posting's start field
+    static constexpr int CHUNK_BYTES = 32;
+    static constexpr int UNIT_BYTES = 32;  // unit of the posting's start field
     struct Chunk { uint4 c, v; };
-    static __device__ __forceinline__ void load(const uint4* p, Chunk& k) { ld_chunk(p, k.c, k.v); }
+    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+        ld_chunk(reinterpret_cast<const uint4*>(p), k.c, k.v);
+    }
     template <class Q>
-    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q) {
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float) {
         if constexpr (Q::HAS_DOT8) {
             return q.dot8(acc, k.c, k.v);
         } else {
@@ -323,16 +325,17 @@ struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x 
     }
 };
 struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16] = 48 bytes = 3 x uint4, unit 16 bytes
-    static constexpr int U = 3;
-    static constexpr int START_MUL = 1;
+    static constexpr int CHUNK_BYTES = 48;
+    static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c0, c1, v; };
-    static __device__ __forceinline__ void load(const uint4* p, Chunk& k) {
-        k.c0 = ld_stream(p);
-        k.c1 = ld_stream(p + 1);
-        k.v = ld_stream(p + 2);
+    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        k.c0 = ld_stream(p4);
+        k.c1 = ld_stream(p4 + 1);
+        k.v = ld_stream(p4 + 2);
     }
     template <class Q>
-    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q) {
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float) {
         acc = q.mac(acc, k.c0.x, k.v.x, false);
         acc = q.mac(acc, k.c0.y, k.v.x, true);
         acc = q.mac(acc, k.c0.z, k.v.y, false);
@@ -344,15 +347,91 @@ struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16
     }
 };
 
+// ---- the other plain value encodings of the reference, u16 components.  value -> f32 exactly as the
+// oracle's decode(): bf16 = bits << 16; f32 as is; fixedu8 / fixedu16 = (float)code * scale (own definition, the
+// reference's FixedU8Q/FixedU16Q scaling lives in vectorium).  These go through the generic per-component
+// q.mac_f path (they are not the benchmark encodings).
+__device__ __forceinline__ float u_to_f32(uint32_t code) {  // exact for code < 2^23, no conversion pipe
+    return __uint_as_float(0x4b000000u | code) - 8388608.f;
+}
+template <int KIND>  // 1 bf16, 4 fixedu16: same 32-byte chunks as Rec16
+struct Rec16V2 {
+    static constexpr int CHUNK_BYTES = 32;
+    static constexpr int UNIT_BYTES = 32;
+    struct Chunk { uint4 c, v; };
+    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+        ld_chunk(reinterpret_cast<const uint4*>(p), k.c, k.v);
+    }
+    static __device__ __forceinline__ float val(uint32_t vw, bool hi, float scale) {
+        if constexpr (KIND == 1) return __uint_as_float(hi ? (vw & 0xffff0000u) : (vw << 16));
+        else return __fmul_rn(u_to_f32(hi ? (vw >> 16) : (vw & 0xffffu)), scale);
+    }
+    template <class Q>
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float scale) {
+        const uint32_t cw[4] = {k.c.x, k.c.y, k.c.z, k.c.w}, vw[4] = {k.v.x, k.v.y, k.v.z, k.v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc = q.mac_f(acc, cw[j] & 0xffffu, val(vw[j], false, scale));
+            acc = q.mac_f(acc, cw[j] >> 16, val(vw[j], true, scale));
+        }
+        return acc;
+    }
+};
+struct Rec16F32 {  // chunk = [8 x u16 | 8 x f32] = 48 bytes, unit 16 bytes
+    static constexpr int CHUNK_BYTES = 48;
+    static constexpr int UNIT_BYTES = 16;
+    struct Chunk { uint4 c, v0, v1; };
+    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(p);
+        k.c = ld_stream(p4);
+        k.v0 = ld_stream(p4 + 1);
+        k.v1 = ld_stream(p4 + 2);
+    }
+    template <class Q>
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float) {
+        acc = q.mac_f(acc, k.c.x & 0xffffu, __uint_as_float(k.v0.x));
+        acc = q.mac_f(acc, k.c.x >> 16, __uint_as_float(k.v0.y));
+        acc = q.mac_f(acc, k.c.y & 0xffffu, __uint_as_float(k.v0.z));
+        acc = q.mac_f(acc, k.c.y >> 16, __uint_as_float(k.v0.w));
+        acc = q.mac_f(acc, k.c.z & 0xffffu, __uint_as_float(k.v1.x));
+        acc = q.mac_f(acc, k.c.z >> 16, __uint_as_float(k.v1.y));
+        acc = q.mac_f(acc, k.c.w & 0xffffu, __uint_as_float(k.v1.z));
+        return q.mac_f(acc, k.c.w >> 16, __uint_as_float(k.v1.w));
+    }
+};
+struct Rec16U8 {  // chunk = [8 x u16 | 8 x u8] = 24 bytes, unit 8 bytes (8-byte loads)
+    static constexpr int CHUNK_BYTES = 24;
+    static constexpr int UNIT_BYTES = 8;
+    struct Chunk { uint2 c0, c1, v; };
+    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+        const uint2* p2 = reinterpret_cast<const uint2*>(p);
+        k.c0 = __ldg(p2);
+        k.c1 = __ldg(p2 + 1);
+        k.v = __ldg(p2 + 2);
+    }
+    template <class Q>
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float scale) {
+        const uint32_t cw[4] = {k.c0.x, k.c0.y, k.c1.x, k.c1.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t vw = j < 2 ? k.v.x : k.v.y;
+            acc = q.mac_f(acc, cw[j] & 0xffffu, __fmul_rn(u_to_f32((vw >> (16 * (j & 1))) & 0xffu), scale));
+            acc = q.mac_f(acc, cw[j] >> 16, __fmul_rn(u_to_f32((vw >> (16 * (j & 1) + 8)) & 0xffu), scale));
+        }
+        return acc;
+    }
+};
+
 // Score one document record (nch chunks at `rec`) with an 8-lane group; lane8 handles chunks
 // lane8, lane8+8, ...  The caller reduces the 8 partial sums with group_reduce.
 template <class R, class Q>
-__device__ __forceinline__ float score_rec(const uint4* __restrict__ rec, uint32_t nch, uint32_t lane8, const Q& q) {
+__device__ __forceinline__ float score_rec(const char* __restrict__ rec, uint32_t nch, uint32_t lane8, const Q& q,
+                                           float scale) {
     float acc = 0.f;
     for (uint32_t m = lane8; m < nch; m += 8) {
         typename R::Chunk k;
-        R::load(rec + R::U * m, k);
-        acc = R::dot(acc, k, q);
+        R::load(rec + (size_t)R::CHUNK_BYTES * m, k);
+        acc = R::dot(acc, k, q, scale);
     }
     return acc;
 }
@@ -366,12 +445,12 @@ __device__ __forceinline__ float group_reduce(float s) {
 // document; all loads of a round are issued before the first use.  `rounds` must be warp-uniform.
 template <int D, class R, class Q>
 __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const uint64_t (&post)[D], uint32_t lane8,
-                                           uint32_t rounds, const Q& q, float (&acc)[D]) {
-    const uint4* rec[D];
+                                           uint32_t rounds, const Q& q, float scale, float (&acc)[D]) {
+    const char* rec[D];
     uint32_t nch[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        rec[j] = fwd + (post[j] >> 16) * R::START_MUL + R::U * lane8;
+        rec[j] = reinterpret_cast<const char*>(fwd) + (post[j] >> 16) * R::UNIT_BYTES + R::CHUNK_BYTES * lane8;
         nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
         acc[j] = 0.f;
     }
@@ -380,10 +459,10 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
         typename R::Chunk k[D];
 #pragma unroll
         for (int j = 0; j < D; ++j)
-            if (m < nch[j]) R::load(rec[j] + R::U * 8 * r, k[j]);
+            if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j]);
 #pragma unroll
         for (int j = 0; j < D; ++j)
-            if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q);
+            if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q, scale);
     }
 }
 
@@ -635,7 +714,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, a.value_scale,
                                  acc, st_units);
             else
-                score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, acc);
+                score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, a.value_scale, acc);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 const float s = group_reduce(acc[j]);

@@ -122,12 +122,19 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
         return SGPU_EINVAL;
     }
     const bool vbyte = v->value_kind == SGPU_VAL_DOTVBYTE;
-    if ((v->comp_bits != 16 && v->comp_bits != 32) || (v->value_kind != SGPU_VAL_F16 && !vbyte) ||
-        (vbyte && (v->comp_bits != 16 || !v->fwd_nnz))) {
-        shost::set_error("sgpu_index_create: supported forward indexes are u16/u32 components with f16 values and "
-                         "u16 DotVByte");
+    if ((v->comp_bits != 16 && v->comp_bits != 32) || v->value_kind > SGPU_VAL_DOTVBYTE ||
+        (v->comp_bits == 32 && v->value_kind != SGPU_VAL_F16) || (vbyte && !v->fwd_nnz)) {
+        shost::set_error("sgpu_index_create: supported forward indexes are u16 components with f16 / bf16 / f32 / "
+                         "fixedu8 / fixedu16 / DotVByte values and u32 components with f16 values");
         return SGPU_EUNSUPPORTED;
     }
+    // record geometry of the plain layouts: chunk = 8 components + 8 values; unit of rec_start / posting starts
+    const uint32_t kind = v->value_kind;
+    const uint32_t val_bytes = kind == SGPU_VAL_F32 ? 4 : (kind == SGPU_VAL_FIXEDU8 ? 1 : 2);
+    const uint32_t chunk_bytes = 8 * ((v->comp_bits == 32 ? 4 : 2) + val_bytes);
+    const uint32_t unit_bytes = chunk_bytes == 32 ? 32 : (chunk_bytes == 48 ? 16 : 8);
+    const uint32_t chunk_units = chunk_bytes / unit_bytes;
+    const bool fast_pack = kind == SGPU_VAL_F16;  // dedicated pack kernels for the two benchmark layouts
     const bool comp32 = v->comp_bits == 32;
     if (v->dim == 0 || (!comp32 && v->dim > 65536) || v->dim > (1u << 20)) {
         shost::set_error("sgpu_index_create: dim must be in [1, 65536] for u16 and [1, 2^20] for u32 components");
@@ -179,15 +186,15 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
                 shost::set_error("document longer than 65535 components");
                 return SGPU_EINVAL;
             }
-            units += ((len + 7) >> 3) * (comp32 ? 3 : 1);
+            units += ((len + 7) >> 3) * chunk_units;
             if (units >= (1ull << 32)) {
                 shost::set_error("forward index larger than 2^32 record units");
                 return SGPU_EUNSUPPORTED;
             }
         }
         rec_start[N] = (uint32_t)units;
-        CK(ix->fwd.ensure(std::max<uint64_t>(units, 1) * (comp32 ? 16 : 32)));
-        total += units * (comp32 ? 16 : 32);
+        CK(ix->fwd.ensure(std::max<uint64_t>(units, 1) * unit_bytes + 64));
+        total += units * unit_bytes;
     }
     if (int rc = upload(ix->rec_start, rec_start.data(), N + 1, st, &total)) return rc;
     DevBuf d_fwd_off;
@@ -205,15 +212,20 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
             if (d1 == d0) d1 = d0 + 1;
             const uint64_t ne = v->fwd_offsets[d1] - e0;
             CK(d_c.ensure(std::max<uint64_t>(ne, 1) * (comp32 ? 4 : 2)));
-            CK(d_v.ensure(std::max<uint64_t>(ne, 1) * 2));
+            CK(d_v.ensure(std::max<uint64_t>(ne, 1) * val_bytes));
             if (ne) {
                 if (comp32) CK(cudaMemcpyAsync(d_c.p, (const uint32_t*)v->fwd_comps + e0, ne * 4, cudaMemcpyHostToDevice, st));
                 else CK(cudaMemcpyAsync(d_c.p, (const uint16_t*)v->fwd_comps + e0, ne * 2, cudaMemcpyHostToDevice, st));
-                CK(cudaMemcpyAsync(d_v.p, (const uint16_t*)v->fwd_values + e0, ne * 2, cudaMemcpyHostToDevice, st));
+                CK(cudaMemcpyAsync(d_v.p, (const uint8_t*)v->fwd_values + e0 * val_bytes, ne * val_bytes,
+                                   cudaMemcpyHostToDevice, st));
             }
             const uint64_t nd = d1 - d0;
             const unsigned blocks = (unsigned)((nd + 7) / 8);
-            if (comp32)
+            if (!fast_pack)
+                k_pack_records_any<<<blocks, 256, 0, st>>>(d_fwd_off.as<uint64_t>(), d_c.as<uint8_t>(), d_v.as<uint8_t>(),
+                                                           ix->rec_start.as<uint32_t>(), d0, nd, e0, ix->fwd.as<uint8_t>(),
+                                                           comp32 ? 4u : 2u, val_bytes, unit_bytes);
+            else if (comp32)
                 k_pack_records32<<<blocks, 256, 0, st>>>(d_fwd_off.as<uint64_t>(), d_c.as<uint32_t>(), d_v.as<uint16_t>(),
                                                          ix->rec_start.as<uint32_t>(), d0, nd, e0, ix->fwd.as<uint32_t>());
             else
@@ -282,6 +294,7 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     d.dim = (uint32_t)dim;
     d.comp32 = comp32 ? 1u : 0u;
     d.vbyte = vbyte ? 1u : 0u;
+    d.value_kind = kind;
     d.value_scale = v->value_scale;
     *out = ix.release();
     return SGPU_OK;
@@ -376,7 +389,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     const bool comp32 = ix->ix.comp32 != 0;
     const bool vbyte = ix->ix.vbyte != 0;
     ad.value_scale = ix->ix.value_scale;
-    const bool dense_ok = !comp32 && !vbyte && smem_d + 1024 <= ix->smem_optin;
+    const uint32_t vkind = ix->ix.value_kind;
+    const bool plain16 = !comp32 && vkind == SGPU_VAL_F16;  // the layouts that also have the dense-query kernel
+    const bool dense_ok = plain16 && smem_d + 1024 <= ix->smem_optin;
     typedef void (*kern_t)(const SearchArgs);
     kern_t kd = small_k ? (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, RegHeap>
                         : (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, SmemHeap>;
@@ -387,8 +402,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ah.first_wave_docs = std::max(1u, ix->hq_first_wave_docs);
     ah.buf_docs = std::max(ah.wave_docs, ah.first_wave_docs);
     ah.counter_idx = 3;
-    const int mode = comp32 ? 3 : (vbyte ? 1 : ix->hq_mode);  // 1 byte index, 2 perfect hash, 3 bitmap + rank
-    const bool wide = comp32 || vbyte || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
+    const int mode = comp32 ? 3 : (!plain16 ? 1 : ix->hq_mode);  // 1 byte index, 2 perfect hash, 3 bitmap + rank
+    const bool wide = !plain16 || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
     const int hq_threads = wide ? 256 : 128;
     size_t qbytes = 0;
     kern_t kh = nullptr;
@@ -401,9 +416,13 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         ah.qd_words = ((ix->ix.dim + 15u) / 16u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 4;
         kh = SGPU_PICK(ByteQuery, 6, 2);
-        if (vbyte)
-            kh = small_k ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, RecVB>
-                         : (kern_t)k_search<256, 4, 2, ByteQuery, SmemHeap, RecVB>;
+#define SGPU_REC(R) (small_k ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, R> : (kern_t)k_search<256, 4, 2, ByteQuery, SmemHeap, R>)
+        if (vkind == SGPU_VAL_DOTVBYTE) kh = SGPU_REC(RecVB);
+        else if (vkind == SGPU_VAL_BF16) kh = SGPU_REC(Rec16V2<1>);
+        else if (vkind == SGPU_VAL_FIXEDU16) kh = SGPU_REC(Rec16V2<4>);
+        else if (vkind == SGPU_VAL_F32) kh = SGPU_REC(Rec16F32);
+        else if (vkind == SGPU_VAL_FIXEDU8) kh = SGPU_REC(Rec16U8);
+#undef SGPU_REC
     } else if (mode == 2) {
         qbytes = (size_t)HQ_SLOTS * 6;
         kh = SGPU_PICK(HashQuery, 6, 2);
@@ -417,7 +436,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     }
 #undef SGPU_PICK
     const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
-    bool hq_ok = (comp32 || vbyte || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
+    bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
     if (hq_ok) {
         CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
@@ -525,7 +544,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         stats->docs_scored = hs[0];
         stats->blocks_scored = hs[1];
         stats->blocks_pushed = hs[2];
-        stats->fwd_bytes = hs[3] * (ix->ix.vbyte ? 1ull : (ix->ix.comp32 ? 48ull : 32ull));
+        const uint64_t cb = 8ull * ((ix->ix.comp32 ? 4 : 2) + (vkind == SGPU_VAL_F32 ? 4 : (vkind == SGPU_VAL_FIXEDU8 ? 1 : 2)));
+        stats->fwd_bytes = hs[3] * (ix->ix.vbyte ? 1ull : cb);
     }
     return SGPU_OK;
 }
@@ -646,7 +666,7 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
         shost::set_error("sgpu_exact_search: bad argument");
         return SGPU_EINVAL;
     }
-    if (ix->ix.comp32 || ix->ix.vbyte) {
+    if (ix->ix.comp32 || ix->ix.value_kind != SGPU_VAL_F16) {
         shost::set_error("sgpu_exact_search: only available for u16/f16 indexes");
         return SGPU_EUNSUPPORTED;
     }

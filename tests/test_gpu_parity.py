@@ -164,6 +164,20 @@ def test_dotvbyte_wide_documents(oracle_mod):
     assert_same(got, ref, "dotvbyte wide docs")
 
 
+@pytest.mark.parametrize("value_kind", [N.VAL_BF16, N.VAL_F32, N.VAL_FIXEDU8, N.VAL_FIXEDU16])
+def test_parity_value_encodings(oracle_mod, value_kind):
+    """The other forward-index value encodings of the reference (SURVEY §8f #1): bf16, f32, fixedu8, fixedu16."""
+    from conftest import build_synth
+    _, q, index = build_synth(20000, 200, dim=3000, n_postings=500, centroid_fraction=0.15, value_kind=value_kind)
+    assert index.value_kind == value_kind
+    g = GpuIndex(index, 0)
+    for k, cut, hf, srt in [(10, 3, 0.8, True), (50, 6, 0.9, False)]:
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        assert_same(got, ref, f"value_kind={value_kind} k={k}")
+        assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
 def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):
     _, q, index = synth_small
     g = GpuIndex(index, 0)
