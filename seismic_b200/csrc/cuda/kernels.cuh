@@ -78,7 +78,7 @@ struct Scratch {
     uint32_t* nterms;    // [nq]
     uint32_t* status;    // [nq] 0 ok, 1 invalid
     float* est;          // [nq_chunk * cut_eff * est_stride]
-    uint16_t* order;     // [nq_chunk * est_stride]
+    uint4* sel;          // [nq_chunk * est_stride] first list in search order: {estimate bits, first posting, postings, block}
     uint32_t* counters;  // [0] dense work counter, [1] max nterms, [2] invalid queries, [3] hq work counter,
                          // [4] number of hq queries, [5] number of dense queries
     uint32_t* hmult;     // [nq] perfect-hash multiplier of the query (0: dense kernel)
@@ -312,7 +312,13 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, S
     const uint32_t l = sc.terms[(uint64_t)q * sc.cut_eff];
     const uint32_t B = ix.lists[l].n_blk;
     const float* est = sc.est + (uint64_t)q * sc.cut_eff * sc.est_stride;
-    uint16_t* out = sc.order + (uint64_t)q * sc.est_stride;
+    uint4* out = sc.sel + (uint64_t)q * sc.est_stride;
+    const uint32_t* boff = ix.blk_post_off + ix.lists[l].blk_base + l;
+    // the search kernel reads one 16-byte entry per position: no dependent order -> estimate -> offsets chain
+    auto emit = [&](uint32_t pos, uint32_t blk) {
+        const uint32_t p0 = boff[blk];
+        out[pos] = make_uint4(__float_as_uint(est[blk]), p0, boff[blk + 1] - p0, blk);
+    };
     if (B <= ORDER_SMEM) {
         uint32_t n2 = 1;
         while (n2 < B) n2 <<= 1;
@@ -332,13 +338,13 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, S
                 }
                 __syncthreads();
             }
-        for (uint32_t i = threadIdx.x; i < B; i += ORDER_THREADS) out[i] = (uint16_t)(s_key[i] & 0xffffu);
+        for (uint32_t i = threadIdx.x; i < B; i += ORDER_THREADS) emit(i, (uint32_t)(s_key[i] & 0xffffu));
     } else {
         for (uint32_t i = threadIdx.x; i < B; i += ORDER_THREADS) {
             const uint64_t mine = ((uint64_t)(~total_key(est[i])) << 32) | i;
             uint32_t rank = 0;
             for (uint32_t j = 0; j < B; ++j) rank += ((((uint64_t)(~total_key(est[j])) << 32) | j) < mine);
-            out[rank] = (uint16_t)i;
+            emit(rank, i);
         }
     }
 }

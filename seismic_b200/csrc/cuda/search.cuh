@@ -87,6 +87,19 @@ __device__ __forceinline__ void ld_chunk(const uint4* p, uint4& c, uint4& v) {
 #endif
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, bypasses L1 and the register file) + group bookkeeping
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr_s) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr_s));
+    return r;
+}
+
 __device__ __forceinline__ float h_lo(uint32_t vw) { return __low2float(*reinterpret_cast<const __half2*>(&vw)); }
 __device__ __forceinline__ float h_hi(uint32_t vw) { return __high2float(*reinterpret_cast<const __half2*>(&vw)); }
 
@@ -549,12 +562,58 @@ struct RegHeap {
     uint32_t n, k;  // warp-uniform
     float theta;    // worst retained score (valid when full)
     uint32_t wkey;
-    __device__ __forceinline__ void reset(uint32_t kk, float*, uint32_t*) {
-        n = 0, k = kk, theta = 0.f, wkey = 0, s = 0.f, key = 0;
+    float* xs;      // k-entry exchange buffers in shared memory (merge32)
+    uint32_t* xk;
+    __device__ __forceinline__ void reset(uint32_t kk, float* bs, uint32_t* bk) {
+        n = 0, k = kk, theta = 0.f, wkey = 0, s = 0.f, key = 0, xs = bs, xk = bk;
     }
     __device__ __forceinline__ bool full() const { return n == k; }
+    // Push the candidates of the lanes in `m` (each can enter the heap as it stands) in ONE step: the result of
+    // pushing a set of items one by one is the k best of (heap U set) whatever the order (total order, strict
+    // replacement), so every item's final position is its rank in the union — counted with pipelined broadcasts
+    // instead of a dependent insertion per item.  Keys within one call must be distinct (a posting list holds a
+    // document once, and one call never spans two lists).
+    __device__ __forceinline__ void merge32(uint32_t m, const float sc, const uint32_t ky, uint32_t lane) {
+        bool c = (m >> lane) & 1u;
+        uint32_t hb = 0;  // retained items better than this lane's candidate
+        bool dup = false;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float hs = __shfl_sync(0xffffffffu, s, i);
+            const uint32_t hk = __shfl_sync(0xffffffffu, key, i);
+            dup |= hk == ky;
+            hb += better(hs, hk, sc, ky);
+        }
+        c = c && !dup;
+        m = __ballot_sync(0xffffffffu, c);
+        uint32_t cb_h = 0, cb_c = 0;  // candidates better than this lane's retained item / candidate
+        for (uint32_t mm = m; mm; mm &= mm - 1) {
+            const int j = __ffs(mm) - 1;
+            const float cs = __shfl_sync(0xffffffffu, sc, j);
+            const uint32_t ck = __shfl_sync(0xffffffffu, ky, j);
+            cb_h += better(cs, ck, s, key);
+            cb_c += better(cs, ck, sc, ky);
+        }
+        const uint32_t rh = lane + cb_h, rc = hb + cb_c;
+        if (lane < n && rh < k) xs[rh] = s, xk[rh] = key;
+        if (c && rc < k) xs[rc] = sc, xk[rc] = ky;
+        __syncwarp();
+        n = min(k, n + (uint32_t)__popc(m));
+        if (lane < n) s = xs[lane], key = xk[lane];
+        __syncwarp();
+        if (n == k) {
+            theta = __shfl_sync(0xffffffffu, s, k - 1);
+            wkey = __shfl_sync(0xffffffffu, key, k - 1);
+        }
+    }
     // push up to 32 items, one per lane; items already retained (same key) are ignored
     __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane) {
+        {
+            const uint32_t m0 = __ballot_sync(0xffffffffu, have && (n < k || better(sc, ky, theta, wkey)));
+            if (__popc(m0) > 2) {
+                merge32(m0, sc, ky, lane);
+                return;
+            }
+        }
         for (;;) {
             const bool c = have && (n < k || better(sc, ky, theta, wkey));
             const uint32_t m = __ballot_sync(0xffffffffu, c);
@@ -649,7 +708,11 @@ struct SmemHeap {
 // T threads per CTA, OCC = CTAs per SM the register allocation is budgeted for, D = documents per 8-lane group
 // per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise),
 // R = record layout (Rec16: u16 components, Rec32: u32 components).
-template <int T, int OCC, int D, class Q, class H, class R = Rec16>
+// RING > 0 (Rec16 only): every warp stages its documents through a private shared-memory ring filled by cp.async —
+// 2 stages x 4 documents (one per 8-lane group) x RING chunks — so the gathers of the next four documents are in
+// flight while the current four are scored, without holding them in registers; chunks beyond RING per document
+// (nnz > 8*RING) are read through registers as before.  Same arithmetic, same order: results are unchanged.
+template <int T, int OCC, int D, class Q, class H, class R = Rec16, int RING = 0>
 __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     constexpr int NW = T / 32;      // warps
     constexpr int GROUPS = T / 8;   // 8-lane groups
@@ -660,15 +723,21 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     uint32_t* cand_end = reinterpret_cast<uint32_t*>(p);  p += T * 4;
     float* cand_est = reinterpret_cast<float*>(p);        p += T * 4;
     uint32_t* cand_p0 = reinterpret_cast<uint32_t*>(p);   p += T * 4;
+    uint32_t* cand_mx = reinterpret_cast<uint32_t*>(p);   p += T * 4;  // total_key of the block's best survivor, 0 = none
     float* heap_s = reinterpret_cast<float*>(p);          p += ((a.k + 3) & ~3u) * 4;
     uint32_t* heap_k = reinterpret_cast<uint32_t*>(p);    p += ((a.k + 3) & ~3u) * 4;
     uint64_t* docs = reinterpret_cast<uint64_t*>(p);      p += (size_t)a.buf_docs * 8;
     float* scores = reinterpret_cast<float*>(p);          p += (size_t)a.buf_docs * 4;
     uint32_t* surv = reinterpret_cast<uint32_t*>(p);  // bit d: document d of the wave can still enter the heap
+    p += ((a.buf_docs + 31) / 32) * 4 + 16;
+    // per-warp staging ring (RING > 0): [2 stages][4 documents][RING chunks of 32 bytes], 128-byte aligned
+    constexpr uint32_t RING_SLOT = RING * 32, RING_STAGE = 4 * RING_SLOT;
+    const uint32_t ring_s =
+        (((uint32_t)__cvta_generic_to_shared(p) + 127u) & ~127u) + (threadIdx.x >> 5) * (2 * RING_STAGE);
 
     __shared__ uint32_t s_q;
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
-    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0;
+    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0, s_quad;
     __shared__ float s_theta;
     __shared__ uint32_t s_full, s_wkey;
     // phase clocks (thread 0 only, kept in shared memory to spare registers):
@@ -695,10 +764,100 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     };
 
     // score docs[0, n) of the wave buffer into scores[] and mark the documents that can still enter the heap
-    auto score_wave = [&](uint32_t n) {
+    // nc > 0: also track the best surviving score of each of the wave's nc candidate blocks (cand_mx)
+    auto score_wave = [&](uint32_t n, uint32_t nc) {
+        auto note_survivor = [&](uint32_t d, float sc) {
+            atomicOr(&surv[d >> 5], 1u << (d & 31));
+            if (nc) {
+                uint32_t lo = 0, hi = nc - 1;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (cand_end[mid] <= d) lo = mid + 1;
+                    else hi = mid;
+                }
+                atomicMax(&cand_mx[lo], total_key(sc));
+            }
+        };
         const bool w_full = s_full != 0;
         const float w_theta = s_theta;
         const uint32_t w_wkey = s_wkey;
+        if constexpr (RING > 0) {
+            static_assert(RING % 4 == 0, "a slot is copied by 8 lanes x 16 bytes per pass");
+            const char* fwd = reinterpret_cast<const char*>(a.ix.fwd);
+            const uint32_t slot_s = ring_s + (lane >> 3) * RING_SLOT;
+            const uint32_t nquads = (n + 3) >> 2;  // 4 documents (one per 8-lane group) per warp stage
+            // start the copies of quad qd into stage b: lane8 copies the 16-byte granules lane8, lane8 + 8, ...
+            auto issue = [&](uint32_t qd, uint32_t b) -> uint64_t {
+                const uint32_t d = qd * 4 + (lane >> 3);
+                const uint64_t post = d < n ? docs[d] : 0ull;  // nnz 0 -> nothing copied, score unused
+                const uint32_t nch = ((uint32_t)(post & 0xffffu) + 7) >> 3;
+                const uint32_t ngran = 2 * min(nch, (uint32_t)RING);
+                const char* src = fwd + (post >> 16) * 32 + 16 * lane8;
+                const uint32_t dst = slot_s + b * RING_STAGE + 16 * lane8;
+#pragma unroll
+                for (int i = 0; i < RING / 4; ++i)
+                    if (lane8 + 8 * i < ngran) cp_async16(dst + 128 * i, src + 128 * i);
+                cp_async_commit();
+                return post;
+            };
+            // quads are handed out dynamically (documents differ 10x in length; a static split leaves warps idle
+            // at the end of the wave); s_quad is zeroed by the caller before the barrier that precedes score_wave
+            auto grab = [&]() -> uint32_t {
+                uint32_t v = 0;
+                if (lane == 0) v = atomicAdd(&s_quad, 1u);
+                return __shfl_sync(0xffffffffu, v, 0);
+            };
+            uint32_t qd = grab(), b = 0;
+            uint64_t post = 0, post_next = 0;
+            if (qd < nquads) post = issue(qd, 0);
+            for (uint32_t qn; qd < nquads; qd = qn, b ^= 1) {
+                qn = grab();
+                if (qn < nquads) {
+                    post_next = issue(qn, b ^ 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+                const uint32_t nnz = (uint32_t)(post & 0xffffu);
+                const uint32_t nch = (nnz + 7) >> 3;
+                const uint32_t rounds = (__reduce_max_sync(0xffffffffu, nnz) + 63) >> 6;
+                const char* rec = fwd + (post >> 16) * 32 + 32 * lane8;
+                // first register round (chunks RING + lane8): issue its loads before the shared-memory rounds
+                typename R::Chunk tail;
+                const bool has_tail = RING + lane8 < nch;
+                if (has_tail) R::load(rec + 32 * RING, tail);
+                float acc = 0.f;
+                const uint32_t src_s = slot_s + b * RING_STAGE + 32 * lane8;
+#pragma unroll
+                for (int r = 0; r < RING / 8; ++r) {
+                    if (lane8 + 8 * r < nch) {
+                        typename R::Chunk kk;
+                        kk.c = lds128(src_s + 256 * r);
+                        kk.v = lds128(src_s + 256 * r + 16);
+                        acc = R::dot(acc, kk, query, a.value_scale);
+                    }
+                }
+                if (has_tail) acc = R::dot(acc, tail, query, a.value_scale);
+                for (uint32_t r = RING / 8 + 1; r < rounds; ++r) {
+                    if (lane8 + 8 * r < nch) {
+                        typename R::Chunk kk;
+                        R::load(rec + 256 * r, kk);
+                        acc = R::dot(acc, kk, query, a.value_scale);
+                    }
+                }
+                const float s = group_reduce(acc);
+                const uint32_t d = qd * 4 + (lane >> 3);
+                if (lane8 == 0 && d < n) {
+                    scores[d] = s;
+                    st_units += nch;
+                    if (!w_full || better(s, (uint32_t)(post >> 16), w_theta, w_wkey)) note_survivor(d, s);
+                }
+                __syncwarp();  // every lane is done with stage b before it is refilled
+                post = post_next;
+            }
+            return;
+        }
         for (uint32_t dbase = 0; dbase < n; dbase += D * GROUPS) {  // CTA-uniform trip count
             uint64_t post[D];
             uint32_t mx = 0;
@@ -723,19 +882,18 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     scores[d] = s;
                     if constexpr (!is_vbyte<R>::value) st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
                     // theta only grows: a document that cannot enter the heap as of the wave start never will
-                    if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey))
-                        atomicOr(&surv[d >> 5], 1u << (d & 31));
+                    if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey)) note_survivor(d, s);
                 }
             }
         }
     };
     // warp 0: offer the surviving documents of wave slots [c0, c1) to the heap
     auto push_range = [&](uint32_t c0, uint32_t c1) {
-        for (uint32_t base = c0 & ~31u; base < c1; base += 32) {
-            const uint32_t i = base + lane;
-            const bool have = i >= c0 && i < c1 && ((surv[base >> 5] >> lane) & 1u);
-            heap.offer(have, have ? scores[i] : 0.f, have ? (uint32_t)(docs[i] >> 16) : 0u, lane);
-        }
+            for (uint32_t base = c0 & ~31u; base < c1; base += 32) {
+                const uint32_t i = base + lane;
+                const bool have = i >= c0 && i < c1 && ((surv[base >> 5] >> lane) & 1u);
+                heap.offer(have, have ? scores[i] : 0.f, have ? (uint32_t)(docs[i] >> 16) : 0u, lane);
+            }
     };
 
     for (;;) {
@@ -759,7 +917,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             const ListHdr h = a.ix.lists[l];
             const uint32_t B = h.n_blk;
             const float* est = a.sc.est + ((uint64_t)q * a.sc.cut_eff + t) * a.sc.est_stride;
-            const uint16_t* ord = (t == 0 && a.first_sorted) ? a.sc.order + (uint64_t)q * a.sc.est_stride : nullptr;
+            const uint4* sel = (t == 0 && a.first_sorted) ? a.sc.sel + (uint64_t)q * a.sc.est_stride : nullptr;
             const uint32_t* boff = a.ix.blk_post_off + h.blk_base + l;
             const uint64_t* posts = a.ix.postings + h.post_base;
             uint32_t pos0 = 0;
@@ -772,14 +930,17 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 bool pass = false;
                 uint32_t nd = 0, p0 = 0;
                 float e = 0.f;
-                if (pos < B) {
-                    const uint32_t blk = ord ? (uint32_t)ord[pos] : pos;
-                    e = est[blk];
-                    pass = !full || !(e < thr);
-                    if (pass) {
-                        p0 = boff[blk];
-                        nd = boff[blk + 1] - p0;
+                if (pos < B) {  // independent loads: one memory round trip per selection pass
+                    if (sel) {
+                        const uint4 se = sel[pos];
+                        e = __uint_as_float(se.x), p0 = se.y, nd = se.z;
+                    } else {
+                        e = est[pos];
+                        p0 = boff[pos];
+                        nd = boff[pos + 1] - p0;
                     }
+                    pass = !full || !(e < thr);
+                    if (!pass) nd = 0;
                 }
                 // block-wide inclusive scans of nd and pass
                 uint32_t cd = nd, cc = pass ? 1u : 0u;
@@ -788,6 +949,12 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     const uint32_t od = __shfl_up_sync(0xffffffffu, cd, sft);
                     const uint32_t oc = __shfl_up_sync(0xffffffffu, cc, sft);
                     if (lane >= (uint32_t)sft) cd += od, cc += oc;
+                }
+                // this block will most likely be in the wave: pull its postings towards L2 ahead of phase 2
+                if (pass && nd && tid < 64 && cd <= cap) {
+                    const char* pp = reinterpret_cast<const char*>(posts + p0);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (size_t)nd * 8 - 8));
                 }
                 if (lane == 31) s_warp_docs[warp] = cd, s_warp_cnt[warp] = cc;
                 if (tid == 0) s_first_rej = 0xffffffffu;
@@ -817,6 +984,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     cand_end[cc - 1] = cd;
                     cand_est[cc - 1] = e;
                     cand_p0[cc - 1] = p0;
+                    cand_mx[cc - 1] = 0u;
                     atomicMax(&s_wave_docs, cd);
                     atomicMax(&s_wave_cnt, cc);
                 }
@@ -830,8 +998,9 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         const uint32_t part = min(a.buf_docs, big_nd - off);
                         for (uint32_t i = tid; i < part; i += T) docs[i] = posts[big_p0 + off + i];
                         for (uint32_t i = tid; i < (part + 31) >> 5; i += T) surv[i] = 0u;
+                        if (tid == 0) s_quad = 0;
                         __syncthreads();
-                        score_wave(part);
+                        score_wave(part, 0);
                         __syncthreads();
                         if (warp == 0) {
                             st_docs += part;
@@ -852,6 +1021,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 // ---------------- phase 2: gather the postings of all candidate blocks into the wave buffer
                 // (flat over document slots; the owning block is found by binary search over cand_end)
                 for (uint32_t i = tid; i < (n_docs + 31) >> 5; i += T) surv[i] = 0u;
+                if (tid == 0) s_quad = 0;
                 for (uint32_t i = tid; i < n_docs; i += T) {
                     uint32_t lo = 0, hi = n_cand - 1;
                     while (lo < hi) {
@@ -865,16 +1035,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 __syncthreads();
                 lap(2);
                 // ---------------- phase 3: score the wave
-                score_wave(n_docs);
-                __syncthreads();
-                // best surviving score of every candidate block (cand_p0 is free again: reuse it as cand_max)
-                float* cand_max = reinterpret_cast<float*>(cand_p0);
-                for (uint32_t j = tid; j < n_cand; j += T) {
-                    float mx = -INFINITY;
-                    for (uint32_t i = j ? cand_end[j - 1] : 0u; i < cand_end[j]; ++i)
-                        if ((surv[i >> 5] >> (i & 31)) & 1u) mx = fmaxf(mx, scores[i]);
-                    cand_max[j] = mx;
-                }
+                score_wave(n_docs, n_cand);
                 __syncthreads();
                 lap(3);
                 // ---------------- phase 4: exact replay by warp 0
@@ -889,8 +1050,8 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         const uint32_t j = j0 + lane;
                         const bool valid = j < n_cand;
                         const uint32_t s0 = valid && j ? cand_end[j - 1] : 0u, s1 = valid ? cand_end[j] : 0u;
-                        const float mx = valid ? cand_max[j] : -INFINITY;
-                        const bool has = mx > -INFINITY && (!heap.full() || mx >= heap.theta);
+                        const uint32_t mx = valid ? cand_mx[j] : 0u;
+                        const bool has = mx != 0u && (!heap.full() || mx >= total_key(heap.theta));
                         const bool passes =
                             valid && !(heap.full() && cand_est[j] < __fmul_rn(a.heap_factor, heap.theta));
                         const uint32_t pm = __ballot_sync(0xffffffffu, passes);

@@ -91,6 +91,7 @@ struct SgpuIndex {
     int hq_enabled = 1, hq_ctas_per_sm = 0;
     int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
     int hq_threads = 256;
+    int hq_ring = 0;  // chunks per document slot of the per-warp cp.async staging ring (0 = off; 8, 16 or 24)
     int hq_occ = 4;   // CTAs per SM the 256-thread compact kernel is compiled for (4: 64 registers, 3: 80 registers)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
@@ -357,12 +358,12 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     const uint32_t cut_eff = std::max(1u, h_counters[1]);
     const uint32_t est_stride = std::max(32u, (ix->max_blocks + 31u) & ~31u);
     // chunk the batch so that the estimate scratch stays within budget
-    const uint64_t per_query = (uint64_t)cut_eff * est_stride * 4 + (uint64_t)est_stride * 2 + (uint64_t)cut_eff * 4 +
+    const uint64_t per_query = (uint64_t)cut_eff * est_stride * 4 + (uint64_t)est_stride * 16 + (uint64_t)cut_eff * 4 +
                                (uint64_t)k * 4 + 12;
     uint32_t chunk = (uint32_t)std::min<uint64_t>(nq, std::max<uint64_t>(1, ix->scratch_bytes / per_query));
     CK(ix->d_terms.ensure((size_t)chunk * cut_eff * 4));
     CK(ix->d_est.ensure((size_t)chunk * cut_eff * est_stride * 4));
-    CK(ix->d_order.ensure((size_t)chunk * est_stride * 2));
+    CK(ix->d_order.ensure((size_t)chunk * est_stride * 16));
     CK(ix->d_keys.ensure((size_t)chunk * k * 4));
     CK(ix->d_hmult.ensure((size_t)chunk * 8));
     CK(ix->d_qlist.ensure((size_t)chunk * 8));
@@ -383,7 +384,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ad.counter_idx = 0;
     const int ctas = std::max(1, ix->ctas);
     auto wave_bytes = [&](const SearchArgs& x, int threads) {
-        return 3 * (size_t)threads * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
+        return 4 * (size_t)threads * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
     };
     const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad, DENSE_THREADS);
     const bool comp32 = ix->ix.comp32 != 0;
@@ -404,8 +405,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ah.counter_idx = 3;
     const int mode = comp32 ? 3 : (!plain16 ? 1 : ix->hq_mode);  // 1 byte index, 2 perfect hash, 3 bitmap + rank
     const bool wide = !plain16 || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
-    const int hq_threads = wide ? 256 : 128;
-    size_t qbytes = 0;
+    int hq_threads = wide ? 256 : 128;
+    size_t qbytes = 0, ring_bytes = 0;
     kern_t kh = nullptr;
 #define SGPU_PICK(Q, OCC128, D128)                                                                        \
     (wide ? (small_k ? (ix->hq_occ == 3 ? (kern_t)k_search<256, 3, 2, Q, RegHeap> : (kern_t)k_search<256, 4, 2, Q, RegHeap>) \
@@ -416,6 +417,24 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         ah.qd_words = ((ix->ix.dim + 15u) / 16u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 4;
         kh = SGPU_PICK(ByteQuery, 6, 2);
+        if (plain16 && wide && small_k && ix->hq_ring > 0) {
+            const int rg = ix->hq_ring >= 24 ? 24 : (ix->hq_ring >= 16 ? 16 : 8), oc = ix->hq_occ;
+            if (ix->hq_threads >= 512 && rg == 16) {
+                hq_threads = 512;
+                kh = (kern_t)k_search<512, 2, 2, ByteQuery, RegHeap, Rec16, 16>;
+            } else if (rg == 24) {
+                kh = oc >= 3 ? (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, 24>
+                             : (kern_t)k_search<256, 2, 2, ByteQuery, RegHeap, Rec16, 24>;
+            } else if (rg == 16) {
+                kh = oc >= 4 ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, Rec16, 16>
+                   : oc == 3 ? (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, 16>
+                             : (kern_t)k_search<256, 2, 2, ByteQuery, RegHeap, Rec16, 16>;
+            } else {
+                kh = oc >= 4 ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, Rec16, 8>
+                             : (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, 8>;
+            }
+            ring_bytes = (size_t)(hq_threads / 32) * 2 * 4 * rg * 32 + 128;
+        }
 #define SGPU_REC(R) (small_k ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, R> : (kern_t)k_search<256, 4, 2, ByteQuery, SmemHeap, R>)
         if (vkind == SGPU_VAL_DOTVBYTE) kh = SGPU_REC(RecVB);
         else if (vkind == SGPU_VAL_BF16) kh = SGPU_REC(Rec16V2<1>);
@@ -435,7 +454,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
                          : (kern_t)k_search<256, 4, 2, RankQuery, SmemHeap, Rec32>;
     }
 #undef SGPU_PICK
-    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
+    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads) + ring_bytes;
     bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
     if (hq_ok) {
@@ -469,7 +488,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         sc.nterms = ix->d_nterms.as<uint32_t>() + q0;
         sc.status = ix->d_status.as<uint32_t>() + q0;
         sc.est = ix->d_est.as<float>();
-        sc.order = ix->d_order.as<uint16_t>();
+        sc.sel = ix->d_order.as<uint4>();
         sc.counters = ix->d_counters.as<uint32_t>();
         sc.hmult = ix->d_hmult.as<uint32_t>();
         sc.cost = ix->d_hmult.as<uint32_t>() + chunk;
@@ -579,6 +598,10 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     if (n == "hq") {  // 0: dense-query kernel only; compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
         ix->hq_enabled = value != 0;
         if (value >= 1 && value <= 3) ix->hq_mode = (int)value;
+        return SGPU_OK;
+    }
+    if (n == "hq_ring") {  // 0 = off
+        ix->hq_ring = (int)std::max<int64_t>(0, value);
         return SGPU_OK;
     }
     if (value <= 0) {
