@@ -43,6 +43,9 @@ constexpr int DENSE_THREADS = 1024;
 #ifndef SGPU_LD256
 #define SGPU_LD256 0
 #endif
+#ifndef SGPU_DOT2X
+#define SGPU_DOT2X 1
+#endif
 #ifndef SGPU_SKIP_MISS
 #define SGPU_SKIP_MISS 1
 #endif
@@ -94,6 +97,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr_s) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr_s));
@@ -173,6 +177,59 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
         acc = __fadd_rn(acc, __fmul_rn(q5, h_hi(v.z)));
         acc = __fadd_rn(acc, __fmul_rn(q6, h_lo(v.w)));
         return __fadd_rn(acc, __fmul_rn(q7, h_hi(v.w)));
+    }
+    // N chunks of one lane in a single basic block: 8N independent index loads, then 8N value loads, then the
+    // (ordered) multiply-add chain — the shared-memory latency is paid twice per call instead of twice per chunk.
+    template <int N>
+    __device__ __forceinline__ float dotn(float acc, const uint4 (&c)[N], const uint4 (&v)[N]) const {
+        uint32_t idx[8 * N];
+        float q[8 * N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const uint32_t cw[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[8 * j + 2 * e]) : "r"(qidx_s + (cw[e] & 0xffffu)));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[8 * j + 2 * e + 1]) : "r"(qidx_s + (cw[e] >> 16)));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8 * N; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q[i]) : "r"(vals_s + idx[i] * 4));
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const uint32_t vw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc = __fadd_rn(acc, __fmul_rn(q[8 * j + 2 * e], h_lo(vw[e])));
+                acc = __fadd_rn(acc, __fmul_rn(q[8 * j + 2 * e + 1], h_hi(vw[e])));
+            }
+        }
+        return acc;
+    }
+    // the same for one chunk of each of two documents (two independent partial sums)
+    __device__ __forceinline__ void dot2x(float& a0, float& a1, const uint4 (&c)[2], const uint4 (&v)[2]) const {
+        uint32_t idx[16];
+        float q[16];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t cw[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[8 * j + 2 * e]) : "r"(qidx_s + (cw[e] & 0xffffu)));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[8 * j + 2 * e + 1]) : "r"(qidx_s + (cw[e] >> 16)));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q[i]) : "r"(vals_s + idx[i] * 4));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t v0 = e == 0 ? v[0].x : e == 1 ? v[0].y : e == 2 ? v[0].z : v[0].w;
+            const uint32_t v1 = e == 0 ? v[1].x : e == 1 ? v[1].y : e == 2 ? v[1].z : v[1].w;
+            a0 = __fadd_rn(a0, __fmul_rn(q[2 * e], h_lo(v0)));
+            a1 = __fadd_rn(a1, __fmul_rn(q[8 + 2 * e], h_lo(v1)));
+            a0 = __fadd_rn(a0, __fmul_rn(q[2 * e + 1], h_hi(v0)));
+            a1 = __fadd_rn(a1, __fmul_rn(q[8 + 2 * e + 1], h_hi(v1)));
+        }
     }
     static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return 1024 + (size_t)a.qd_words * 4; }
     __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
@@ -319,6 +376,7 @@ struct RankQuery {
 // ---- forward-index record layouts ---------------------------------------------------------------------------
 // A record is a sequence of chunks of 8 (component, value) pairs; the posting's start field counts UNIT-byte units.
 struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x uint4, unit 32 bytes
+    static constexpr bool PLAIN_F16 = true;
     static constexpr int CHUNK_BYTES = 32;
     static constexpr int UNIT_BYTES = 32;  // unit of the posting's start field
     struct Chunk { uint4 c, v; };
@@ -338,6 +396,7 @@ struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x 
     }
 };
 struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16] = 48 bytes = 3 x uint4, unit 16 bytes
+    static constexpr bool PLAIN_F16 = false;
     static constexpr int CHUNK_BYTES = 48;
     static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c0, c1, v; };
@@ -369,6 +428,7 @@ __device__ __forceinline__ float u_to_f32(uint32_t code) {  // exact for code < 
 }
 template <int KIND>  // 1 bf16, 4 fixedu16: same 32-byte chunks as Rec16
 struct Rec16V2 {
+    static constexpr bool PLAIN_F16 = false;
     static constexpr int CHUNK_BYTES = 32;
     static constexpr int UNIT_BYTES = 32;
     struct Chunk { uint4 c, v; };
@@ -391,6 +451,7 @@ struct Rec16V2 {
     }
 };
 struct Rec16F32 {  // chunk = [8 x u16 | 8 x f32] = 48 bytes, unit 16 bytes
+    static constexpr bool PLAIN_F16 = false;
     static constexpr int CHUNK_BYTES = 48;
     static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c, v0, v1; };
@@ -413,6 +474,7 @@ struct Rec16F32 {  // chunk = [8 x u16 | 8 x f32] = 48 bytes, unit 16 bytes
     }
 };
 struct Rec16U8 {  // chunk = [8 x u16 | 8 x u8] = 24 bytes, unit 8 bytes (8-byte loads)
+    static constexpr bool PLAIN_F16 = false;
     static constexpr int CHUNK_BYTES = 24;
     static constexpr int UNIT_BYTES = 8;
     struct Chunk { uint2 c0, c1, v; };
@@ -469,13 +531,24 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
     }
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t m = lane8 + 8 * r;
-        typename R::Chunk k[D];
+        if constexpr (SGPU_DOT2X && D == 2 && Q::HAS_DOT8 && R::CHUNK_BYTES == 32 && R::PLAIN_F16) {
+            // both documents in one basic block; a chunk past the end of a record is (0, +0.0) x 8: adds q * 0 = +-0
+            uint4 c[2], v[2];
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-            if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j]);
+            for (int j = 0; j < 2; ++j) {
+                c[j] = make_uint4(0, 0, 0, 0), v[j] = make_uint4(0, 0, 0, 0);
+                if (m < nch[j]) ld_chunk(reinterpret_cast<const uint4*>(rec[j] + (size_t)256 * r), c[j], v[j]);
+            }
+            q.dot2x(acc[0], acc[1], c, v);
+        } else {
+            typename R::Chunk k[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-            if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q, scale);
+            for (int j = 0; j < D; ++j)
+                if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j]);
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q, scale);
+        }
     }
 }
 
@@ -807,13 +880,26 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 if (lane == 0) v = atomicAdd(&s_quad, 1u);
                 return __shfl_sync(0xffffffffu, v, 0);
             };
-            uint32_t qd = grab(), b = 0;
+            // pull the records of quad qd towards L2 (one 128-byte line per lane: the first 1 KB of each document)
+            auto l2pf = [&](uint32_t qd) {
+                const uint32_t d = qd * 4 + (lane >> 3);
+                if (d < n) {
+                    const uint64_t post = docs[d];
+                    if (lane8 * 16 < (uint32_t)(post & 0xffffu))
+                        prefetch_l2(fwd + (post >> 16) * 32 + 128 * lane8);
+                }
+            };
+            // three quads per warp in the pipe: qd is scored from shared memory, q1's cp.async copies are in flight
+            // (they find their lines in L2), q2's lines are on their way from DRAM to L2
+            uint32_t qd = grab(), q1 = grab(), b = 0;
             uint64_t post = 0, post_next = 0;
             if (qd < nquads) post = issue(qd, 0);
-            for (uint32_t qn; qd < nquads; qd = qn, b ^= 1) {
-                qn = grab();
-                if (qn < nquads) {
-                    post_next = issue(qn, b ^ 1);
+            l2pf(q1);
+            for (uint32_t q2; qd < nquads; qd = q1, q1 = q2, b ^= 1) {
+                q2 = grab();
+                l2pf(q2);
+                if (q1 < nquads) {
+                    post_next = issue(q1, b ^ 1);
                     cp_async_wait<1>();
                 } else {
                     cp_async_wait<0>();
@@ -829,13 +915,28 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 if (has_tail) R::load(rec + 32 * RING, tail);
                 float acc = 0.f;
                 const uint32_t src_s = slot_s + b * RING_STAGE + 32 * lane8;
+                if constexpr (Q::HAS_DOT8 && RING == 16) {
+                    // both staged rounds in one basic block; a chunk past the end of the record is (0, +0.0) x 8,
+                    // which adds q * 0 = +-0 to the partial sum and leaves it bit-identical
+                    uint4 cc[2], vv[2];
 #pragma unroll
-                for (int r = 0; r < RING / 8; ++r) {
-                    if (lane8 + 8 * r < nch) {
-                        typename R::Chunk kk;
-                        kk.c = lds128(src_s + 256 * r);
-                        kk.v = lds128(src_s + 256 * r + 16);
-                        acc = R::dot(acc, kk, query, a.value_scale);
+                    for (int r = 0; r < 2; ++r) {
+                        cc[r] = make_uint4(0, 0, 0, 0), vv[r] = make_uint4(0, 0, 0, 0);
+                        if (lane8 + 8 * r < nch) {
+                            cc[r] = lds128(src_s + 256 * r);
+                            vv[r] = lds128(src_s + 256 * r + 16);
+                        }
+                    }
+                    acc = query.template dotn<2>(acc, cc, vv);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RING / 8; ++r) {
+                        if (lane8 + 8 * r < nch) {
+                            typename R::Chunk kk;
+                            kk.c = lds128(src_s + 256 * r);
+                            kk.v = lds128(src_s + 256 * r + 16);
+                            acc = R::dot(acc, kk, query, a.value_scale);
+                        }
                     }
                 }
                 if (has_tail) acc = R::dot(acc, tail, query, a.value_scale);
@@ -859,6 +960,17 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             return;
         }
         for (uint32_t dbase = 0; dbase < n; dbase += D * GROUPS) {  // CTA-uniform trip count
+            if constexpr (!is_vbyte<R>::value && D == 2) {
+                // the next iteration's records -> L2 (lane: document lane8 / 4, 128-byte lines lane8 % 4 and + 4)
+                const uint32_t dn = dbase + D * GROUPS + (lane8 >> 2) * GROUPS + grp;
+                if (dn < n) {
+                    const uint64_t pn = docs[dn];
+                    const uint32_t bytes = (((uint32_t)(pn & 0xffffu) + 7) >> 3) * R::CHUNK_BYTES, ln = (lane8 & 3) * 128;
+                    const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pn >> 16) * R::UNIT_BYTES;
+                    if (ln < bytes) prefetch_l2(base + ln);
+                    if (ln + 512 < bytes) prefetch_l2(base + ln + 512);
+                }
+            }
             uint64_t post[D];
             uint32_t mx = 0;
 #pragma unroll
@@ -1030,7 +1142,15 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         else hi = mid;
                     }
                     const uint32_t start = lo ? cand_end[lo - 1] : 0u;
-                    docs[i] = posts[cand_p0[lo] + (i - start)];
+                    const uint64_t pst = posts[cand_p0[lo] + (i - start)];
+                    docs[i] = pst;
+                    if constexpr (!is_vbyte<R>::value) {
+                        if (i < T / 4) {  // what the first scoring step of every warp reads: start the DRAM access now
+                            const uint32_t bytes = (((uint32_t)(pst & 0xffffu) + 7) >> 3) * R::CHUNK_BYTES;
+                            const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pst >> 16) * R::UNIT_BYTES;
+                            for (uint32_t o = 0; o < bytes && o < 1024; o += 128) prefetch_l2(base + o);
+                        }
+                    }
                 }
                 __syncthreads();
                 lap(2);
