@@ -124,13 +124,15 @@ typedef struct SgpuSearchStats {
     float ms_search;         /* Loop B: persistent traversal/scoring/top-k kernel               */
     float ms_finish;         /* key -> doc id mapping                                           */
     uint32_t n_launches;     /* kernels launched by the call                                    */
-    uint32_t reserved;
+    uint32_t ctas_per_sm;    /* resident CTAs per SM of the compact-query k_search launch        */
     uint64_t docs_scored;    /* forward-index vectors actually read (incl. speculative ones)    */
     uint64_t blocks_scored;  /* blocks whose docs were read                                     */
     uint64_t blocks_pushed;  /* blocks that survived the exact replay (== reference evaluated)  */
     uint64_t fwd_bytes;      /* bytes of forward-index records read                             */
     uint64_t phase_cycles[6];/* SM clocks summed over CTAs: fetch+stage, select, gather postings,
                                 score, replay, results (k_search's own phase profile)           */
+    uint64_t waves;          /* waves of documents scored (k_search)                            */
+    uint64_t select_passes;  /* candidate-selection passes (k_search)                           */
 } SgpuSearchStats;
 
 typedef struct SgpuIndex SgpuIndex; /* opaque: HBM image + scratch + stream on one device        */

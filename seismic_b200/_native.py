@@ -79,12 +79,13 @@ class SearchParams(C.Structure):
 
 class SearchStats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_prep", C.c_float), ("ms_summary", C.c_float), ("ms_search", C.c_float),
-                ("ms_finish", C.c_float), ("n_launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("ms_finish", C.c_float), ("n_launches", C.c_uint32), ("ctas_per_sm", C.c_uint32),
                 ("docs_scored", C.c_uint64), ("blocks_scored", C.c_uint64), ("blocks_pushed", C.c_uint64),
-                ("fwd_bytes", C.c_uint64), ("phase_cycles", C.c_uint64 * 6)]
+                ("fwd_bytes", C.c_uint64), ("phase_cycles", C.c_uint64 * 6), ("waves", C.c_uint64),
+                ("select_passes", C.c_uint64)]
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in ("reserved", "phase_cycles")}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "phase_cycles"}
         d["phase_cycles"] = list(self.phase_cycles)
         return d
 
@@ -157,14 +158,20 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if _stale():
+    override = os.environ.get("SEISMIC_B200_LIB")  # A/B runs of two builds on one GPU box (tools/variants.py)
+    if override:
+        path = Path(override)
+    elif _stale():
+        path = LIB_PATH
         if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
             build_native()
         elif not LIB_PATH.exists():
             raise ImportError(
                 "seismic_b200: native library %s is missing and nvcc is not available; "
                 "run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
-    handle = C.CDLL(str(LIB_PATH))
+    else:
+        path = LIB_PATH
+    handle = C.CDLL(str(path))
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(handle, name)
         fn.restype = res

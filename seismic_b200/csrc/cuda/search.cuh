@@ -90,20 +90,7 @@ __device__ __forceinline__ void ld_chunk(const uint4* p, uint4& c, uint4& v) {
 #endif
 }
 
-// 16-byte asynchronous global -> shared copy (LDGSTS, bypasses L1 and the register file) + group bookkeeping
-__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ uint4 lds128(uint32_t addr_s) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr_s));
-    return r;
-}
-
 __device__ __forceinline__ float h_lo(uint32_t vw) { return __low2float(*reinterpret_cast<const __half2*>(&vw)); }
 __device__ __forceinline__ float h_hi(uint32_t vw) { return __high2float(*reinterpret_cast<const __half2*>(&vw)); }
 
@@ -178,35 +165,8 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
         acc = __fadd_rn(acc, __fmul_rn(q6, h_lo(v.w)));
         return __fadd_rn(acc, __fmul_rn(q7, h_hi(v.w)));
     }
-    // N chunks of one lane in a single basic block: 8N independent index loads, then 8N value loads, then the
-    // (ordered) multiply-add chain — the shared-memory latency is paid twice per call instead of twice per chunk.
-    template <int N>
-    __device__ __forceinline__ float dotn(float acc, const uint4 (&c)[N], const uint4 (&v)[N]) const {
-        uint32_t idx[8 * N];
-        float q[8 * N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const uint32_t cw[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[8 * j + 2 * e]) : "r"(qidx_s + (cw[e] & 0xffffu)));
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[8 * j + 2 * e + 1]) : "r"(qidx_s + (cw[e] >> 16)));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8 * N; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q[i]) : "r"(vals_s + idx[i] * 4));
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const uint32_t vw[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                acc = __fadd_rn(acc, __fmul_rn(q[8 * j + 2 * e], h_lo(vw[e])));
-                acc = __fadd_rn(acc, __fmul_rn(q[8 * j + 2 * e + 1], h_hi(vw[e])));
-            }
-        }
-        return acc;
-    }
-    // the same for one chunk of each of two documents (two independent partial sums)
+    // One chunk of each of two documents in a single basic block: 16 independent index loads, then 16 value loads,
+    // then the two (ordered) multiply-add chains — the shared-memory latency is paid twice per call, not per chunk.
     __device__ __forceinline__ void dot2x(float& a0, float& a1, const uint4 (&c)[2], const uint4 (&v)[2]) const {
         uint32_t idx[16];
         float q[16];
@@ -781,11 +741,7 @@ struct SmemHeap {
 // T threads per CTA, OCC = CTAs per SM the register allocation is budgeted for, D = documents per 8-lane group
 // per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise),
 // R = record layout (Rec16: u16 components, Rec32: u32 components).
-// RING > 0 (Rec16 only): every warp stages its documents through a private shared-memory ring filled by cp.async —
-// 2 stages x 4 documents (one per 8-lane group) x RING chunks — so the gathers of the next four documents are in
-// flight while the current four are scored, without holding them in registers; chunks beyond RING per document
-// (nnz > 8*RING) are read through registers as before.  Same arithmetic, same order: results are unchanged.
-template <int T, int OCC, int D, class Q, class H, class R = Rec16, int RING = 0>
+template <int T, int OCC, int D, class Q, class H, class R = Rec16>
 __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     constexpr int NW = T / 32;      // warps
     constexpr int GROUPS = T / 8;   // 8-lane groups
@@ -802,20 +758,16 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     uint64_t* docs = reinterpret_cast<uint64_t*>(p);      p += (size_t)a.buf_docs * 8;
     float* scores = reinterpret_cast<float*>(p);          p += (size_t)a.buf_docs * 4;
     uint32_t* surv = reinterpret_cast<uint32_t*>(p);  // bit d: document d of the wave can still enter the heap
-    p += ((a.buf_docs + 31) / 32) * 4 + 16;
-    // per-warp staging ring (RING > 0): [2 stages][4 documents][RING chunks of 32 bytes], 128-byte aligned
-    constexpr uint32_t RING_SLOT = RING * 32, RING_STAGE = 4 * RING_SLOT;
-    const uint32_t ring_s =
-        (((uint32_t)__cvta_generic_to_shared(p) + 127u) & ~127u) + (threadIdx.x >> 5) * (2 * RING_STAGE);
 
     __shared__ uint32_t s_q;
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
-    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0, s_quad;
+    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0;
     __shared__ float s_theta;
     __shared__ uint32_t s_full, s_wkey;
     // phase clocks (thread 0 only, kept in shared memory to spare registers):
-    // 0 fetch+stage, 1 select, 2 gather postings, 3 score, 4 replay, 5 results, [6] = last mark
-    __shared__ long long s_ph[7];
+    // 0 fetch+stage, 1 select, 2 gather postings, 3 score, 4 replay, 5 results
+    __shared__ uint32_t s_ph[6];
+    __shared__ uint32_t s_cnt[2];  // waves scored, selection passes
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lane8 = tid & 7, grp = tid >> 3;
@@ -826,14 +778,19 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     uint32_t st_docs = 0, st_blocks = 0, st_pushed = 0, st_units = 0;  // per-CTA totals fit 32 bits
     if (tid == 0) {
         for (int i = 0; i < 6; ++i) s_ph[i] = 0;
-        s_ph[6] = clock64();
+        s_cnt[0] = s_cnt[1] = 0;
     }
+    // Phase clock of thread 0.  Deliberately branch-free (one predicated reduction): an `if (tid == 0)` block can
+    // leave thread 0 split from its warp across the code that follows, and every shuffle / vote there then takes its
+    // divergent slow path (seen with ncu on a variant of this kernel: 4x slower replay).
+    uint32_t t_last = (uint32_t)clock();
+    const uint32_t ph_s = (uint32_t)__cvta_generic_to_shared(s_ph);
     auto lap = [&](int i) {
-        if (tid == 0) {
-            const long long now = clock64();
-            s_ph[i] += now - s_ph[6];
-            s_ph[6] = now;
-        }
+        const uint32_t now = (uint32_t)clock();
+        asm volatile("{ .reg .pred p; setp.eq.u32 p, %0, 0; @p red.shared.add.u32 [%1], %2; }" ::"r"(tid),
+                     "r"(ph_s + 4 * i), "r"(now - t_last)
+                     : "memory");
+        t_last = now;
     };
 
     // score docs[0, n) of the wave buffer into scores[] and mark the documents that can still enter the heap
@@ -854,111 +811,6 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         const bool w_full = s_full != 0;
         const float w_theta = s_theta;
         const uint32_t w_wkey = s_wkey;
-        if constexpr (RING > 0) {
-            static_assert(RING % 4 == 0, "a slot is copied by 8 lanes x 16 bytes per pass");
-            const char* fwd = reinterpret_cast<const char*>(a.ix.fwd);
-            const uint32_t slot_s = ring_s + (lane >> 3) * RING_SLOT;
-            const uint32_t nquads = (n + 3) >> 2;  // 4 documents (one per 8-lane group) per warp stage
-            // start the copies of quad qd into stage b: lane8 copies the 16-byte granules lane8, lane8 + 8, ...
-            auto issue = [&](uint32_t qd, uint32_t b) -> uint64_t {
-                const uint32_t d = qd * 4 + (lane >> 3);
-                const uint64_t post = d < n ? docs[d] : 0ull;  // nnz 0 -> nothing copied, score unused
-                const uint32_t nch = ((uint32_t)(post & 0xffffu) + 7) >> 3;
-                const uint32_t ngran = 2 * min(nch, (uint32_t)RING);
-                const char* src = fwd + (post >> 16) * 32 + 16 * lane8;
-                const uint32_t dst = slot_s + b * RING_STAGE + 16 * lane8;
-#pragma unroll
-                for (int i = 0; i < RING / 4; ++i)
-                    if (lane8 + 8 * i < ngran) cp_async16(dst + 128 * i, src + 128 * i);
-                cp_async_commit();
-                return post;
-            };
-            // quads are handed out dynamically (documents differ 10x in length; a static split leaves warps idle
-            // at the end of the wave); s_quad is zeroed by the caller before the barrier that precedes score_wave
-            auto grab = [&]() -> uint32_t {
-                uint32_t v = 0;
-                if (lane == 0) v = atomicAdd(&s_quad, 1u);
-                return __shfl_sync(0xffffffffu, v, 0);
-            };
-            // pull the records of quad qd towards L2 (one 128-byte line per lane: the first 1 KB of each document)
-            auto l2pf = [&](uint32_t qd) {
-                const uint32_t d = qd * 4 + (lane >> 3);
-                if (d < n) {
-                    const uint64_t post = docs[d];
-                    if (lane8 * 16 < (uint32_t)(post & 0xffffu))
-                        prefetch_l2(fwd + (post >> 16) * 32 + 128 * lane8);
-                }
-            };
-            // three quads per warp in the pipe: qd is scored from shared memory, q1's cp.async copies are in flight
-            // (they find their lines in L2), q2's lines are on their way from DRAM to L2
-            uint32_t qd = grab(), q1 = grab(), b = 0;
-            uint64_t post = 0, post_next = 0;
-            if (qd < nquads) post = issue(qd, 0);
-            l2pf(q1);
-            for (uint32_t q2; qd < nquads; qd = q1, q1 = q2, b ^= 1) {
-                q2 = grab();
-                l2pf(q2);
-                if (q1 < nquads) {
-                    post_next = issue(q1, b ^ 1);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncwarp();
-                const uint32_t nnz = (uint32_t)(post & 0xffffu);
-                const uint32_t nch = (nnz + 7) >> 3;
-                const uint32_t rounds = (__reduce_max_sync(0xffffffffu, nnz) + 63) >> 6;
-                const char* rec = fwd + (post >> 16) * 32 + 32 * lane8;
-                // first register round (chunks RING + lane8): issue its loads before the shared-memory rounds
-                typename R::Chunk tail;
-                const bool has_tail = RING + lane8 < nch;
-                if (has_tail) R::load(rec + 32 * RING, tail);
-                float acc = 0.f;
-                const uint32_t src_s = slot_s + b * RING_STAGE + 32 * lane8;
-                if constexpr (Q::HAS_DOT8 && RING == 16) {
-                    // both staged rounds in one basic block; a chunk past the end of the record is (0, +0.0) x 8,
-                    // which adds q * 0 = +-0 to the partial sum and leaves it bit-identical
-                    uint4 cc[2], vv[2];
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        cc[r] = make_uint4(0, 0, 0, 0), vv[r] = make_uint4(0, 0, 0, 0);
-                        if (lane8 + 8 * r < nch) {
-                            cc[r] = lds128(src_s + 256 * r);
-                            vv[r] = lds128(src_s + 256 * r + 16);
-                        }
-                    }
-                    acc = query.template dotn<2>(acc, cc, vv);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < RING / 8; ++r) {
-                        if (lane8 + 8 * r < nch) {
-                            typename R::Chunk kk;
-                            kk.c = lds128(src_s + 256 * r);
-                            kk.v = lds128(src_s + 256 * r + 16);
-                            acc = R::dot(acc, kk, query, a.value_scale);
-                        }
-                    }
-                }
-                if (has_tail) acc = R::dot(acc, tail, query, a.value_scale);
-                for (uint32_t r = RING / 8 + 1; r < rounds; ++r) {
-                    if (lane8 + 8 * r < nch) {
-                        typename R::Chunk kk;
-                        R::load(rec + 256 * r, kk);
-                        acc = R::dot(acc, kk, query, a.value_scale);
-                    }
-                }
-                const float s = group_reduce(acc);
-                const uint32_t d = qd * 4 + (lane >> 3);
-                if (lane8 == 0 && d < n) {
-                    scores[d] = s;
-                    st_units += nch;
-                    if (!w_full || better(s, (uint32_t)(post >> 16), w_theta, w_wkey)) note_survivor(d, s);
-                }
-                __syncwarp();  // every lane is done with stage b before it is refilled
-                post = post_next;
-            }
-            return;
-        }
         for (uint32_t dbase = 0; dbase < n; dbase += D * GROUPS) {  // CTA-uniform trip count
             if constexpr (!is_vbyte<R>::value && D == 2) {
                 // the next iteration's records -> L2 (lane: document lane8 / 4, 128-byte lines lane8 % 4 and + 4)
@@ -1035,6 +887,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             uint32_t pos0 = 0;
             while (pos0 < B) {
                 // ---------------- phase 1: candidate selection over positions [pos0, pos0 + T)
+                if (tid == 0) ++s_cnt[1];
                 const bool full = s_full != 0;
                 const float thr = __fmul_rn(a.heap_factor, s_theta);
                 const uint32_t cap = first_wave ? a.first_wave_docs : a.wave_docs;
@@ -1110,7 +963,6 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         const uint32_t part = min(a.buf_docs, big_nd - off);
                         for (uint32_t i = tid; i < part; i += T) docs[i] = posts[big_p0 + off + i];
                         for (uint32_t i = tid; i < (part + 31) >> 5; i += T) surv[i] = 0u;
-                        if (tid == 0) s_quad = 0;
                         __syncthreads();
                         score_wave(part, 0);
                         __syncthreads();
@@ -1133,7 +985,6 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 // ---------------- phase 2: gather the postings of all candidate blocks into the wave buffer
                 // (flat over document slots; the owning block is found by binary search over cand_end)
                 for (uint32_t i = tid; i < (n_docs + 31) >> 5; i += T) surv[i] = 0u;
-                if (tid == 0) s_quad = 0;
                 for (uint32_t i = tid; i < n_docs; i += T) {
                     uint32_t lo = 0, hi = n_cand - 1;
                     while (lo < hi) {
@@ -1162,6 +1013,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 if (warp == 0) {
                     st_docs += n_docs;
                     st_blocks += n_cand;
+                    if (lane == 0) ++s_cnt[0];
                     // 32 candidate blocks at a time: a block whose best surviving score cannot enter the live heap
                     // only needs the skip test (counted, heap untouched); the first block that can AND passes the
                     // test against the live theta is pushed, which may raise theta, so the scan restarts after it.
@@ -1209,6 +1061,8 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         atomicAdd(&a.sc.stats[2], (unsigned long long)st_pushed);
         atomicAdd(&a.sc.stats[3], (unsigned long long)st_units);
         for (int i = 0; i < 6; ++i) atomicAdd(&a.sc.stats[4 + i], (unsigned long long)s_ph[i]);
+        atomicAdd(&a.sc.stats[10], (unsigned long long)s_cnt[0]);
+        atomicAdd(&a.sc.stats[11], (unsigned long long)s_cnt[1]);
     }
 }
 

@@ -74,7 +74,7 @@ struct PinnedBuf {
 struct SgpuIndex {
     int device = 0;
     int n_sm = 0;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     cudaStream_t stream = nullptr;      // stream all work is enqueued on
     cudaStream_t own_stream = nullptr;  // the library's private stream
     cudaEvent_t ev[8] = {};
@@ -91,7 +91,7 @@ struct SgpuIndex {
     int hq_enabled = 1, hq_ctas_per_sm = 0;
     int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
     int hq_threads = 256;
-    int hq_ring = 0;  // chunks per document slot of the per-warp cp.async staging ring (0 = off; 8, 16 or 24)
+    int hq_carveout_pct = 0;  // shared-memory carveout of the compact kernel in % of the SM maximum (0: smallest that fits)
     int hq_occ = 4;   // CTAs per SM the 256-thread compact kernel is compiled for (4: 64 registers, 3: 80 registers)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
@@ -157,6 +157,9 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     int optin = 0;
     CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     ix->smem_optin = (size_t)optin;
+    int per_sm = 0;
+    CK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+    ix->smem_per_sm = (size_t)per_sm;
     ix->ctas = ix->n_sm;
     CK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
@@ -335,9 +338,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     CK(ix->d_nterms.ensure((size_t)nq * 4));
     CK(ix->d_status.ensure((size_t)nq * 4));
     CK(ix->d_counters.ensure(32));
-    CK(ix->d_stats.ensure(10 * sizeof(unsigned long long)));
+    CK(ix->d_stats.ensure(12 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ix->d_counters.p, 0, 32, st));
-    CK(cudaMemsetAsync(ix->d_stats.p, 0, 10 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ix->d_stats.p, 0, 12 * sizeof(unsigned long long), st));
 
     CK(cudaEventRecord(ix->ev[0], st));
     Batch all{dq->offsets, dq->comps, dq->values, nq, 0};
@@ -405,8 +408,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ah.counter_idx = 3;
     const int mode = comp32 ? 3 : (!plain16 ? 1 : ix->hq_mode);  // 1 byte index, 2 perfect hash, 3 bitmap + rank
     const bool wide = !plain16 || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
-    int hq_threads = wide ? 256 : 128;
-    size_t qbytes = 0, ring_bytes = 0;
+    const int hq_threads = wide ? 256 : 128;
+    size_t qbytes = 0;
     kern_t kh = nullptr;
 #define SGPU_PICK(Q, OCC128, D128)                                                                        \
     (wide ? (small_k ? (ix->hq_occ == 3 ? (kern_t)k_search<256, 3, 2, Q, RegHeap> : (kern_t)k_search<256, 4, 2, Q, RegHeap>) \
@@ -417,24 +420,6 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         ah.qd_words = ((ix->ix.dim + 15u) / 16u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 4;
         kh = SGPU_PICK(ByteQuery, 6, 2);
-        if (plain16 && wide && small_k && ix->hq_ring > 0) {
-            const int rg = ix->hq_ring >= 24 ? 24 : (ix->hq_ring >= 16 ? 16 : 8), oc = ix->hq_occ;
-            if (ix->hq_threads >= 512 && rg == 16) {
-                hq_threads = 512;
-                kh = (kern_t)k_search<512, 2, 2, ByteQuery, RegHeap, Rec16, 16>;
-            } else if (rg == 24) {
-                kh = oc >= 3 ? (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, 24>
-                             : (kern_t)k_search<256, 2, 2, ByteQuery, RegHeap, Rec16, 24>;
-            } else if (rg == 16) {
-                kh = oc >= 4 ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, Rec16, 16>
-                   : oc == 3 ? (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, 16>
-                             : (kern_t)k_search<256, 2, 2, ByteQuery, RegHeap, Rec16, 16>;
-            } else {
-                kh = oc >= 4 ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, Rec16, 8>
-                             : (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, 8>;
-            }
-            ring_bytes = (size_t)(hq_threads / 32) * 2 * 4 * rg * 32 + 128;
-        }
 #define SGPU_REC(R) (small_k ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, R> : (kern_t)k_search<256, 4, 2, ByteQuery, SmemHeap, R>)
         if (vkind == SGPU_VAL_DOTVBYTE) kh = SGPU_REC(RecVB);
         else if (vkind == SGPU_VAL_BF16) kh = SGPU_REC(Rec16V2<1>);
@@ -454,16 +439,26 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
                          : (kern_t)k_search<256, 4, 2, RankQuery, SmemHeap, Rec32>;
     }
 #undef SGPU_PICK
-    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads) + ring_bytes;
+    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
     bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
+    uint32_t ctas_per_sm = 0;
     if (hq_ok) {
         CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kh, hq_threads, smem_h));
         if (ix->hq_ctas_per_sm > 0) occ = std::min(occ, ix->hq_ctas_per_sm);
+        // Shared memory and L1 share one 256 KB array and the in-flight gathers live in L1: ask for the smallest
+        // shared-memory carveout that still holds `occ` CTAs (measured: a 228 KB carveout costs 20 % on k_search)
+        cudaFuncAttributes fa{};
+        CK(cudaFuncGetAttributes(&fa, kh));
+        const size_t need = (size_t)occ * (smem_h + fa.sharedSizeBytes + 1024);
+        int pct = ix->hq_carveout_pct > 0 ? ix->hq_carveout_pct
+                                          : (int)std::min<size_t>(100, (need * 100 + ix->smem_per_sm - 1) / ix->smem_per_sm);
+        CK(cudaFuncSetAttribute(kh, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         hq_ok = occ >= 1;
         hq_ctas = occ * ix->n_sm;
+        ctas_per_sm = (uint32_t)occ;
     }
     if (!hq_ok && !dense_ok) {
         shost::set_error("neither the compact-query nor the dense-query kernel fits this index in shared memory");
@@ -551,7 +546,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     if (stats) {
         float ms_prep = 0.f;
         CK(cudaEventElapsedTime(&ms_prep, ix->ev[0], ix->ev[1]));
-        unsigned long long hs[10];
+        unsigned long long hs[12];
         CK(cudaMemcpy(hs, ix->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost));
         for (int i = 0; i < 6; ++i) stats->phase_cycles[i] = hs[4 + i];
         stats->ms_prep = ms_prep + ms_terms;
@@ -560,9 +555,12 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         stats->ms_finish = ms_fin;
         stats->ms_total = stats->ms_prep + ms_sum + ms_search + ms_fin;
         stats->n_launches = launches;
+        stats->ctas_per_sm = ctas_per_sm;
         stats->docs_scored = hs[0];
         stats->blocks_scored = hs[1];
         stats->blocks_pushed = hs[2];
+        stats->waves = hs[10];
+        stats->select_passes = hs[11];
         const uint64_t cb = 8ull * ((ix->ix.comp32 ? 4 : 2) + (vkind == SGPU_VAL_F32 ? 4 : (vkind == SGPU_VAL_FIXEDU8 ? 1 : 2)));
         stats->fwd_bytes = hs[3] * (ix->ix.vbyte ? 1ull : cb);
     }
@@ -600,16 +598,13 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
         if (value >= 1 && value <= 3) ix->hq_mode = (int)value;
         return SGPU_OK;
     }
-    if (n == "hq_ring") {  // 0 = off
-        ix->hq_ring = (int)std::max<int64_t>(0, value);
-        return SGPU_OK;
-    }
     if (value <= 0) {
         shost::set_error("option values must be positive");
         return SGPU_EINVAL;
     }
     if (n == "hq_threads") ix->hq_threads = (int)value;
     else if (n == "hq_occ") ix->hq_occ = (int)value;
+    else if (n == "hq_carveout_pct") ix->hq_carveout_pct = (int)value;
     else if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
     else if (n == "hq_first_wave_docs") ix->hq_first_wave_docs = (uint32_t)value;
     else if (n == "hq_ctas_per_sm") ix->hq_ctas_per_sm = (int)value;

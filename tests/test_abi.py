@@ -43,7 +43,7 @@ def test_struct_layouts_match_header(native):
     assert ctypes.sizeof(native.IndexView) == 32 + 16 * 8
     assert ctypes.sizeof(native.QueryBatch) == 32
     assert ctypes.sizeof(native.SearchParams) == 20
-    assert ctypes.sizeof(native.SearchStats) == 28 + 4 + 32 + 48
+    assert ctypes.sizeof(native.SearchStats) == 28 + 4 + 32 + 48 + 16
     assert ctypes.sizeof(native.SynthConfig) == 56
 
 

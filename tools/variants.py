@@ -2,7 +2,7 @@
 """Build the benchmark index once and time k_search under several kernel-option sets (GPU box).
 
 Every option set must return the same ids / score bits as the first one (results never depend on tuning knobs).
-usage: tools/variants.py --docs 1000000 "hq_ring=0" "hq_ring=16,hq_occ=3,hq_wave_docs=640" ...
+usage: tools/variants.py --docs 1000000 "hq_occ=4" "hq_occ=3,hq_wave_docs=640" ...
 """
 import argparse, json, sys, time
 from pathlib import Path
@@ -27,7 +27,7 @@ index = HostIndex.build(docs); del docs
 q = Dataset.synth_queries(cfg, a.queries)
 print("setup s", round(time.time() - t, 1), flush=True)
 gpu = GpuIndex(index, 0)
-defaults = {"hq_ring": 0, "hq_occ": 4, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "hq_threads": 256}
+defaults = {"hq_occ": 4, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "hq_threads": 256}
 base = None
 rows = []
 for opt in a.opts:
@@ -50,7 +50,7 @@ for opt in a.opts:
                     and np.array_equal(cnt, base[2]))
         tot = float(sum(best["phase_cycles"])) or 1.0
         row = {"opts": opt, "ms_search": round(best["ms_search"], 3), "ms_total": round(best["ms_total"], 3),
-               "same_results": same, "docs_scored": best["docs_scored"],
+               "same_results": same, "docs_scored": best["docs_scored"], "ctas_per_sm": best.get("ctas_per_sm"), "waves": best.get("waves"), "passes": best.get("select_passes"),
                "phase_share": [round(c / tot, 3) for c in best["phase_cycles"]]}
     except Exception as e:  # e.g. a configuration that does not fit shared memory
         row = {"opts": opt, "error": str(e)[:200]}
