@@ -65,6 +65,7 @@ struct SearchArgs {
     uint32_t wave_docs;        // soft cap of documents per wave
     uint32_t first_wave_docs;  // soft cap for the first wave of a query (heap still empty)
     uint32_t buf_docs;         // capacity of the wave buffers (>= wave caps); larger blocks are split
+    uint32_t cand_cap;         // capacity of the per-wave candidate-block arrays (<= threads per CTA)
     uint32_t qd_words;         // 32-bit words of the query table (meaning depends on the query type)
     float value_scale;         // DotVByte: value = code * value_scale
     float* out_scores;         // [nq*k] (chunk-relative)
@@ -749,10 +750,10 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     Q query;
     query.template init<T>(smem_raw, a, threadIdx.x);
     unsigned char* p = smem_raw + ((Q::bytes(a) + 15) & ~(size_t)15);
-    uint32_t* cand_end = reinterpret_cast<uint32_t*>(p);  p += T * 4;
-    float* cand_est = reinterpret_cast<float*>(p);        p += T * 4;
-    uint32_t* cand_p0 = reinterpret_cast<uint32_t*>(p);   p += T * 4;
-    uint32_t* cand_mx = reinterpret_cast<uint32_t*>(p);   p += T * 4;  // total_key of the block's best survivor, 0 = none
+    uint32_t* cand_end = reinterpret_cast<uint32_t*>(p);  p += a.cand_cap * 4;
+    float* cand_est = reinterpret_cast<float*>(p);        p += a.cand_cap * 4;
+    uint32_t* cand_p0 = reinterpret_cast<uint32_t*>(p);   p += a.cand_cap * 4;
+    uint32_t* cand_mx = reinterpret_cast<uint32_t*>(p);   p += a.cand_cap * 4;  // total_key of the block's best survivor, 0 = none
     float* heap_s = reinterpret_cast<float*>(p);          p += ((a.k + 3) & ~3u) * 4;
     uint32_t* heap_k = reinterpret_cast<uint32_t*>(p);    p += ((a.k + 3) & ~3u) * 4;
     uint64_t* docs = reinterpret_cast<uint64_t*>(p);      p += (size_t)a.buf_docs * 8;
@@ -939,7 +940,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 if (warp > 0) cd += s_warp_docs[warp - 1], cc += s_warp_cnt[warp - 1];
                 // accept while the wave stays within its soft cap; the first passing block is accepted whenever it
                 // fits the buffer; a first passing block larger than the buffer is processed alone, in parts
-                const bool accepted = pass && cd <= (cc == 1 ? a.buf_docs : cap);
+                const bool accepted = pass && cd <= (cc == 1 ? a.buf_docs : cap) && cc <= a.cand_cap;
                 if (pass && !accepted) atomicMin(&s_first_rej, pos);
                 if (pass && cc == 1 && !accepted) s_big_nd = nd, s_big_p0 = p0;
                 __syncthreads();

@@ -91,6 +91,7 @@ struct SgpuIndex {
     int hq_enabled = 1, hq_ctas_per_sm = 0;
     int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
     int hq_threads = 256;
+    int hq_cand_cap = 256;    // candidate blocks per wave of the compact kernel
     int hq_carveout_pct = 0;  // shared-memory carveout of the compact kernel in % of the SM maximum (0: smallest that fits)
     int hq_occ = 4;   // CTAs per SM the 256-thread compact kernel is compiled for (4: 64 registers, 3: 80 registers)
     int ctas = 0;
@@ -383,11 +384,12 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ad.wave_docs = std::max(1u, ix->wave_docs);
     ad.first_wave_docs = std::max(1u, ix->first_wave_docs);
     ad.buf_docs = std::max(ad.wave_docs, ad.first_wave_docs);
+    ad.cand_cap = DENSE_THREADS;
     ad.qd_words = (ix->ix.dim + 31u) & ~31u;
     ad.counter_idx = 0;
     const int ctas = std::max(1, ix->ctas);
-    auto wave_bytes = [&](const SearchArgs& x, int threads) {
-        return 4 * (size_t)threads * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
+    auto wave_bytes = [&](const SearchArgs& x, int) {
+        return 4 * (size_t)x.cand_cap * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
     };
     const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad, DENSE_THREADS);
     const bool comp32 = ix->ix.comp32 != 0;
@@ -439,6 +441,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
                          : (kern_t)k_search<256, 4, 2, RankQuery, SmemHeap, Rec32>;
     }
 #undef SGPU_PICK
+    ah.cand_cap = (uint32_t)std::min(hq_threads, std::max(32, ((ix->hq_cand_cap + 3) / 4) * 4));
     const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
     bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
@@ -598,13 +601,17 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
         if (value >= 1 && value <= 3) ix->hq_mode = (int)value;
         return SGPU_OK;
     }
+    if (n == "hq_carveout_pct") {  // 0 = automatic
+        ix->hq_carveout_pct = (int)std::min<int64_t>(100, std::max<int64_t>(0, value));
+        return SGPU_OK;
+    }
     if (value <= 0) {
         shost::set_error("option values must be positive");
         return SGPU_EINVAL;
     }
     if (n == "hq_threads") ix->hq_threads = (int)value;
     else if (n == "hq_occ") ix->hq_occ = (int)value;
-    else if (n == "hq_carveout_pct") ix->hq_carveout_pct = (int)value;
+    else if (n == "hq_cand_cap") ix->hq_cand_cap = (int)value;
     else if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
     else if (n == "hq_first_wave_docs") ix->hq_first_wave_docs = (uint32_t)value;
     else if (n == "hq_ctas_per_sm") ix->hq_ctas_per_sm = (int)value;
