@@ -51,12 +51,13 @@ def parse_args():
     ap.add_argument("--centroid-fraction", type=float, default=0.1)
     ap.add_argument("--summary-energy", type=float, default=0.4)
     ap.add_argument("--max-fraction", type=float, default=1.5)
-    ap.add_argument("--recall-queries", type=int, default=256, help="queries used for recall@k vs exact (0 = skip)")
+    ap.add_argument("--recall-queries", type=int, default=1000, help="queries used for recall@k vs exact (0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=2000, help="queries of the CPU baseline sample")
     ap.add_argument("--wave-docs", type=int, default=0)
     ap.add_argument("--first-wave-docs", type=int, default=0)
-    ap.add_argument("--r97-cut", type=int, default=5, help="query_cut of the extra run that reaches recall@10 >= 0.97")
-    ap.add_argument("--r97-hf", type=float, default=0.9)
+    ap.add_argument("--r97", default="5:0.9,6:0.9,5:0.8,8:0.9",
+                    help="query_cut:heap_factor candidates, cheapest first, for the extra run that must reach "
+                         "recall@10 >= 0.97 (the first that does is reported); empty = skip")
     ap.add_argument("--keep-index", action="store_true")
     return ap.parse_args()
 
@@ -341,20 +342,24 @@ def main():
         # not a tuned point of the reference and reaches ~0.95 on this corpus, so the nearest config
         # that does reach 0.97 is measured too (same batch, device-resident inputs, CUDA events of the library).
         r97 = None
-        if a.recall_queries > 0 and a.r97_cut > 0:
+        for cand in filter(None, a.r97.split(",") if a.recall_queries > 0 else []):
+            cut97, hf97 = int(cand.split(":")[0]), float(cand.split(":")[1])
             ms = []
             for i in range(3 + min(a.steps, 20)):
-                st97 = gpu.batch_search_device(d_off.data_ptr(), d_c.data_ptr(), d_v.data_ptr(), nq, k, a.r97_cut,
-                                               a.r97_hf, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                st97 = gpu.batch_search_device(d_off.data_ptr(), d_c.data_ptr(), d_v.data_ptr(), nq, k, cut97, hf97,
+                                               d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
                                                first_sorted=bool(a.sorted))
                 if i >= 3:
                     ms.append(st97["ms_total"])
             torch.cuda.synchronize()
             ids97 = d_ids.cpu().numpy().view(np.uint64)
             cnt97 = d_cnt.cpu().numpy().view(np.uint32)
-            r97 = {"query_cut": a.r97_cut, "heap_factor": a.r97_hf, "recall_at_k": recall_at_k(ex[0], ex[2], ids97[:nr], cnt97[:nr]),
-                   "value": world * nq / (float(np.mean(ms)) * 1e-3), "unit": "queries/s (sum of kernel times, per-GPU x n_gpus)",
-                   "ms_per_step": float(np.mean(ms))}
+            r97 = {"query_cut": cut97, "heap_factor": hf97, "recall_at_k": recall_at_k(ex[0], ex[2], ids97[:nr], cnt97[:nr]),
+                   "recall_queries": nr, "value": world * nq / (float(np.mean(ms)) * 1e-3),
+                   "unit": "queries/s (sum of kernel times, per-GPU x n_gpus)", "ms_per_step": float(np.mean(ms)),
+                   "ms_search": float(st97["ms_search"])}
+            if r97["recall_at_k"] >= 0.97:
+                break
         ms_search = float(np.mean([s["ms_search"] for s in stats]))
         ms_kernels = float(np.mean([s["ms_total"] for s in stats]))
         alg_search = ost["bytes_postings"] + ost["bytes_forward"] + ost["bytes_query_out"]
@@ -400,7 +405,7 @@ def main():
             "clocks": clocks,
             "parity": {"queries": nq, "id_mismatch_queries_host_api": mism, "id_mismatch_queries_device_api": mism_dev,
                        "scores_bit_identical": score_ok},
-            "recall_at_k": recall,
+            "recall_at_k": recall, "recall_queries": min(a.recall_queries, nq),
             "at_recall_0.97": r97,
             "kernel_ms": {k2: float(np.mean([s[k2] for s in stats])) for k2 in
                           ("ms_prep", "ms_summary", "ms_search", "ms_finish", "ms_total")},
@@ -408,6 +413,7 @@ def main():
                      "blocks_scored_gpu": int(stats[-1]["blocks_scored"]), "blocks_evaluated_reference": int(ost["blocks_evaluated"]),
                      "algorithmic_bytes_per_query": ost["bytes_total"] / nq},
             "phase_share": (lambda c: [round(x / max(1, sum(c)), 4) for x in c])(stats[-1]["phase_cycles"]),
+            "waves_per_query": round(stats[-1].get("waves", 0) / nq, 2), "ctas_per_sm": stats[-1].get("ctas_per_sm"),
             "setup_s": timings, "wall_s_timed_region": t_wall, "ms_kernels_per_step": ms_kernels,
         }
         emit(out)
