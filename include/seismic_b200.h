@@ -69,7 +69,7 @@ typedef struct SgpuIndexView {
     uint64_t n_docs;      /* forward_index.len()                                               */
     uint64_t dim;         /* number of posting lists == forward_index.input_dim()              */
     float value_scale;    /* FIXEDU8/FIXEDU16/DOTVBYTE: value = code * value_scale; else 1     */
-    uint32_t reserved0;
+    uint32_t knn_dim;     /* Knn::dim: neighbours stored per document; 0 = no kNN graph        */
 
     /* forward index.  Units of fwd_offsets: elements (plain encodings) or BYTES of the packed
      * stream (DOTVBYTE).  Doc i = [fwd_offsets[i], fwd_offsets[i+1]).                          */
@@ -96,6 +96,11 @@ typedef struct SgpuIndexView {
                                      /*   list_sc_start[l]+l, relative to list_ent_start[l]     */
     const uint16_t* ent_blk;         /* [TE] summaries_ids (block id inside its list)           */
     const uint8_t* ent_code;         /* [TE] values (u8 codes)                                  */
+
+    /* optional kNN graph == Knn{n_vecs, dim, neighbours} src/inverted_index.rs:430-434 with the BitField
+     * decoded: row d holds the knn_dim neighbours of document d, best first; SGPU_PAD_ID = no neighbour
+     * (the reference cannot represent a short row: it concatenates the rows, :487-491).  NULL = none.  */
+    const uint64_t* knn_neighbours;  /* [n_docs * knn_dim]                                      */
 } SgpuIndexView;
 
 /* A batch of sparse queries in CSR form.  Components must be non-decreasing inside a query
@@ -112,7 +117,7 @@ typedef struct SgpuSearchParams {
     uint32_t k;
     uint32_t query_cut;
     float heap_factor;
-    uint32_t n_knn;        /* must be 0 in this release (Knn::refine is SURVEY §8f "next")      */
+    uint32_t n_knn;        /* > 0: Knn::refine with min(n_knn, knn_dim) neighbours (needs a graph) */
     int32_t first_sorted;  /* Python default True (src/pylib/mod.rs:497-498), CLI default false */
 } SgpuSearchParams;
 
@@ -165,6 +170,12 @@ int sgpu_batch_search_device(SgpuIndex* index, const SgpuQueryBatch* d_queries, 
 /* Enqueue all work of this index on `cuda_stream` (a cudaStream_t of the index's device, e.g. the caller's
  * torch stream) instead of the library's private stream; NULL restores the private stream. */
 int sgpu_index_set_stream(SgpuIndex* index, void* cuda_stream);
+
+/* Attach, replace or (neighbours == NULL) drop the kNN graph used by Knn::refine (src/inverted_index.rs:551-593):
+ * `neighbours` is a HOST array [n_docs * knn_dim] of document ids, row d = neighbours of document d, best first,
+ * SGPU_PAD_ID = none.  Replaces Knn::new_from_serialized / InvertedIndex::add_knn (src/inverted_index.rs:494-549)
+ * on the device side.  Not available for DotVByte indexes (the reference class has no kNN, src/pylib/dotvbyte.rs). */
+int sgpu_index_set_knn(SgpuIndex* index, const uint64_t* neighbours, uint32_t knn_dim);
 
 /* Tuning knobs (do not change results): wave sizes of the speculative block scheduler, CTA count.
  * name in {"wave_docs","first_wave_docs","ctas","scratch_mb"}; returns SGPU_EINVAL for unknown. */

@@ -404,6 +404,29 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
             }
         }
     }
+    if (p.n_knn > 0) {
+        // Knn::refine (src/inverted_index.rs:551-593): snapshot of the heap, best first; for each retained document
+        // its first min(dim, n_knn) graph neighbours; unvisited ones are scored and pushed.
+        const uint32_t n_knn = std::min<uint32_t>(v.knn_dim, p.n_knn);
+        KHeap copy = heap;  // heap.clone().into_sorted_vec()
+        const std::vector<Item> snap = copy.into_sorted_vec();
+        for (const Item& it : snap) {
+            const uint64_t* ub = std::upper_bound(v.fwd_offsets, v.fwd_offsets + v.n_docs + 1, fwd_pos(v, it.start));
+            const uint64_t id = (uint64_t)(ub - v.fwd_offsets) - 1;  // id_from_range
+            for (uint32_t i = 0; i < n_knn; ++i) {
+                const uint64_t nb = v.knn_neighbours[id * v.knn_dim + i];
+                if (nb >= v.n_docs) continue;  // SGPU_PAD_ID: no neighbour (see include/seismic_b200.h)
+                const uint64_t start = v.fwd_offsets[nb];  // range_from_id
+                const uint32_t len = (uint32_t)(v.fwd_offsets[nb + 1] - start);
+                if (len == 0) continue;  // an empty document is never a search result, hence never a neighbour
+                if (cx.visited.insert(start)) {
+                    st.docs_scored++;
+                    st.bytes_forward += (uint64_t)len * (cbytes + vbytes);
+                    heap.push(Item{doc_score<ORDER>(v, q, start, len), start, len});
+                }
+            }
+        }
+    }
     std::vector<Item> res = heap.into_sorted_vec();
     *out_count = (uint32_t)res.size();
     st.results += res.size();
@@ -425,7 +448,8 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
 
 int validate(const SgpuIndexView* v, const SgpuQueryBatch* qb, const SgpuSearchParams* p) {
     if (!v || !qb || !p || p->k == 0) return SGPU_EINVAL;
-    if (p->n_knn != 0) return SGPU_EUNSUPPORTED;
+    if (p->n_knn != 0 && (!v->knn_neighbours || v->knn_dim == 0)) return SGPU_EINVAL;
+    if (p->n_knn != 0 && v->value_kind == SGPU_VAL_DOTVBYTE) return SGPU_EUNSUPPORTED;  // no kNN on DotVByte
     if (v->value_kind == SGPU_VAL_DOTVBYTE && (v->comp_bits != 16 || !v->fwd_nnz)) return SGPU_EUNSUPPORTED;
     for (uint64_t qi = 0; qi < qb->n_queries; ++qi)
         for (uint64_t i = qb->offsets[qi]; i < qb->offsets[qi + 1]; ++i) {

@@ -59,12 +59,13 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 class IndexView(C.Structure):
     _fields_ = [
         ("comp_bits", C.c_uint32), ("value_kind", C.c_uint32), ("n_docs", C.c_uint64), ("dim", C.c_uint64),
-        ("value_scale", C.c_float), ("reserved0", C.c_uint32),
+        ("value_scale", C.c_float), ("knn_dim", C.c_uint32),
         ("fwd_offsets", C.c_void_p), ("fwd_comps", C.c_void_p), ("fwd_values", C.c_void_p), ("fwd_nnz", C.c_void_p),
         ("list_post_start", C.c_void_p), ("postings", C.c_void_p), ("list_blk_start", C.c_void_p),
         ("blk_post_off", C.c_void_p), ("blk_min", C.c_void_p), ("blk_quant", C.c_void_p),
         ("list_sc_start", C.c_void_p), ("sc_comp", C.c_void_p), ("list_ent_start", C.c_void_p),
         ("sc_run_off", C.c_void_p), ("ent_blk", C.c_void_p), ("ent_code", C.c_void_p),
+        ("knn_neighbours", C.c_void_p),
     ]
 
 
@@ -119,6 +120,7 @@ SYMBOLS = {
                                            C.c_void_p, C.c_void_p, C.POINTER(SearchStats)]),
     "sgpu_index_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgpu_index_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "sgpu_index_set_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "sgpu_exact_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_float)]),
     "sgpu_last_error": (C.c_char_p, []),

@@ -109,7 +109,8 @@ class _IndexBase:
 
     @property
     def knn_len(self) -> int:
-        return 0
+        """Neighbours per document of the attached kNN graph, 0 if none (src/inverted_index.rs:421-426)."""
+        return 0 if self._host.knn is None else int(self._host.knn.shape[1])
 
     @property
     def is_empty(self) -> bool:
@@ -141,18 +142,72 @@ class _IndexBase:
         print("\t  ├─ packed_postings: %d Bytes (%.2f%%)" % (u["packed_postings"], pct(u["packed_postings"])))
         print("\t  ├─ block_offsets: %d Bytes (%.2f%%)" % (u["block_offsets"], pct(u["block_offsets"])))
         print("\t  └─ summaries: %d Bytes (%.2f%%)" % (u["summaries"], pct(u["summaries"])))
-        print("\tKnn: 0 Bytes")
+        print("\tKnn: %d Bytes" % (0 if self._host.knn is None else self._host.knn.nbytes))
         print("\tTotal: %d Bytes" % u["total"])
 
-    # -- kNN graph: SURVEY §8(f) "next" row 2, not in this release
-    def build_knn(self, nknn: int) -> None:
-        raise NotImplementedError("Knn::refine / build_knn is not implemented in this release (SURVEY.md §8f)")
+    # -- kNN graph (reference Knn, src/inverted_index.rs:430-593; Python surface src/pylib/mod.rs:224-291)
+    _KNN_QUERY_CUT, _KNN_HEAP_FACTOR = 10, 0.7  # src/inverted_index.rs:456-457
+    _KNN_MAGIC = b"SB2KNN01"
+
+    def _attach_knn(self, neighbours: Optional[np.ndarray]) -> None:
+        self._host.set_knn(neighbours)
+        if self._gpu is not None:
+            self._gpu.set_knn(neighbours)
+
+    def build_knn(self, nknn: int, batch_docs: int = 200_000) -> None:
+        """Knn::new (src/inverted_index.rs:448-500): every document searches the index with its own vector
+        (k = nknn + 1, query_cut 10, heap_factor 0.7, no refine, unsorted), drops itself and keeps nknn results.
+        The N self-searches run as GPU batches.  A row with fewer than nknn results is padded with PAD_ID (the
+        reference concatenates the rows, which only works when every row is full)."""
+        if nknn <= 0:
+            raise ValueError("nknn must be > 0")
+        n = self._host.len
+        out = np.full((n, nknn), N.PAD_ID, dtype=np.uint64)
+        for lo in range(0, n, batch_docs):
+            hi = min(n, lo + batch_docs)
+            off, comps, vals = self._host.forward_csr(lo, hi)
+            ids, _, counts = self.gpu.batch_search(off, comps, vals, nknn + 1, self._KNN_QUERY_CUT,
+                                                   self._KNN_HEAP_FACTOR, 0, False)
+            me = np.arange(lo, hi, dtype=np.uint64)[:, None]
+            keep = (ids != me) & (np.arange(nknn + 1)[None, :] < counts[:, None])
+            # stable compaction of every row to its first nknn kept entries
+            order = np.argsort(~keep, axis=1, kind="stable")[:, :nknn]
+            rows = np.take_along_axis(ids, order, axis=1)
+            rows[~np.take_along_axis(keep, order, axis=1)] = N.PAD_ID
+            out[lo:hi] = rows
+        self._attach_knn(out)
 
     def save_knn(self, path: str) -> None:
-        raise ValueError("No kNN graph to save")  # reference: PyValueError when no graph (src/pylib/mod.rs:260-264)
+        """Writes <path>.knn.seismic (Knn::serialize, src/inverted_index.rs:542-548).  Own flat format (the reference's
+        byte encoding lives in vectorium): magic, n_vecs u64, dim u64, then n_vecs * dim u64 ids."""
+        knn = self._host.knn
+        if knn is None:
+            raise ValueError("No KNN graph is attached to the index.")  # PyValueError, src/pylib/mod.rs:260-264
+        try:
+            with open(path + ".knn.seismic", "wb") as f:
+                f.write(self._KNN_MAGIC)
+                f.write(np.array(knn.shape, dtype=np.uint64).tobytes())
+                f.write(np.ascontiguousarray(knn).tobytes())
+        except OSError:
+            raise
+        except Exception as e:
+            raise OSError(str(e))
 
     def load_knn(self, knn_path: str, nknn: Optional[int] = None) -> None:
-        raise NotImplementedError("kNN graphs are not implemented in this release (SURVEY.md §8f)")
+        """Knn::new_from_serialized (src/inverted_index.rs:502-540): optionally keep only the first nknn neighbours."""
+        with open(knn_path, "rb") as f:
+            if f.read(8) != self._KNN_MAGIC:
+                raise OSError("%s is not a kNN file of this library" % knn_path)
+            n_vecs, dim = (int(x) for x in np.frombuffer(f.read(16), dtype=np.uint64))
+            nb = np.frombuffer(f.read(n_vecs * dim * 8), dtype=np.uint64).reshape(n_vecs, dim)
+        if n_vecs != self._host.len:
+            raise ValueError("kNN file holds %d vectors, the index %d" % (n_vecs, self._host.len))
+        if nknn is not None:
+            if nknn > dim:  # assert in the reference, src/inverted_index.rs:513-516
+                raise ValueError("The number of neighbors to include for each vector of the dataset can't be greater "
+                                 "than the number of neighbours in the precomputed knn file.")
+            nb = nb[:, :nknn]
+        self._attach_knn(np.ascontiguousarray(nb))
 
     # -- GPU
     def to_device(self, device: int = 0) -> "GpuIndex":
@@ -175,10 +230,14 @@ class _IndexBase:
                            summary_energy=summary_energy, max_fraction=max_fraction, doc_cut=doc_cut,
                            comp_bits=cls._COMP_BITS, value_kind=cls._VALUE_KIND, n_threads=num_threads)
 
-    @staticmethod
-    def _check_knn_args(nknn, knn_path):
-        if nknn or knn_path:
-            raise NotImplementedError("nknn / knn_path: kNN graphs are not implemented in this release")
+    def _apply_knn_args(self, nknn, knn_path):
+        """KnnConfiguration of build (src/pylib/mod.rs:349-352, src/inverted_index.rs:654-685): a precomputed file
+        wins over building; nknn then limits the neighbours read from it."""
+        if knn_path:
+            self.load_knn(knn_path, nknn if nknn else None)
+        elif nknn:
+            self.build_knn(nknn)
+        return self
 
 
 # ------------------------------------------------------------------------------------------ SeismicDataset
@@ -278,7 +337,6 @@ class SeismicIndex(_IndexBase):
               summary_energy: float = 0.4, max_fraction: float = 1.5, doc_cut: int = 15, nknn: int = 0,
               knn_path: Optional[str] = None, batched_indexing: Optional[int] = None,
               input_token_to_id_map: Optional[Dict[str, int]] = None, load_content: bool = True, num_threads: int = 0):
-        cls._check_knn_args(nknn, knn_path)
         try:
             token_to_id, doc_ids, contents, comps, vals = _read_collection(
                 input_path, dict(input_token_to_id_map) if input_token_to_id_map else None, load_content,
@@ -287,17 +345,16 @@ class SeismicIndex(_IndexBase):
             raise OSError(str(e))
         ds = Dataset.from_lists(comps, vals, dim=max(1, len(token_to_id)))
         cfg = cls._config(n_postings, centroid_fraction, min_cluster_size, summary_energy, max_fraction, doc_cut, num_threads)
-        return cls(cls._build_host(ds, cfg), doc_ids, token_to_id, contents)
+        return cls(cls._build_host(ds, cfg), doc_ids, token_to_id, contents)._apply_knn_args(nknn, knn_path)
 
     @classmethod
     def build_from_dataset(cls, dataset: SeismicDataset, n_postings: int = 3500, centroid_fraction: float = 0.1,
                            min_cluster_size: int = 2, summary_energy: float = 0.4, max_fraction: float = 1.5,
                            doc_cut: int = 15, nknn: int = 0, knn_path: Optional[str] = None,
                            batched_indexing: Optional[int] = None, num_threads: int = 0):
-        cls._check_knn_args(nknn, knn_path)
         cfg = cls._config(n_postings, centroid_fraction, min_cluster_size, summary_energy, max_fraction, doc_cut, num_threads)
         return cls(cls._build_host(dataset._native(), cfg), list(dataset._doc_ids), dict(dataset._token_to_id),
-                   list(dataset._contents))
+                   list(dataset._contents))._apply_knn_args(nknn, knn_path)
 
     @classmethod
     def _build_host(cls, ds: Dataset, cfg: N.BuildConfig) -> HostIndex:
@@ -379,8 +436,17 @@ class SeismicIndexDotVByte(SeismicIndex):
         host = HostIndex.build(ds, cfg)
         return host.convert_to_dotvbyte()
 
-    def build_knn(self, nknn: int) -> None:  # the reference class has no build_knn (src/pylib/dotvbyte.rs:101-112)
+    # the reference class has no kNN methods (src/pylib/dotvbyte.rs:101-112)
+    def build_knn(self, nknn: int, batch_docs: int = 0) -> None:
         raise AttributeError("SeismicIndexDotVByte has no build_knn")
+
+    def load_knn(self, knn_path: str, nknn: Optional[int] = None) -> None:
+        raise AttributeError("SeismicIndexDotVByte has no load_knn")
+
+    def _apply_knn_args(self, nknn, knn_path):
+        if nknn or knn_path:
+            raise ValueError("SeismicIndexDotVByte does not support kNN graphs")
+        return self
 
 
 # ------------------------------------------------------------------------------------------ Raw indexes
@@ -392,10 +458,9 @@ class SeismicIndexRaw(_IndexBase):
     def build(cls, input_file: str, n_postings: int = 3500, centroid_fraction: float = 0.1, min_cluster_size: int = 2,
               summary_energy: float = 0.4, max_fraction: float = 1.5, doc_cut: int = 15, nknn: int = 0,
               knn_path: Optional[str] = None, batched_indexing: Optional[int] = None):
-        cls._check_knn_args(nknn, knn_path)
         ds = Dataset.read_bin(input_file)
         cfg = cls._config(n_postings, centroid_fraction, min_cluster_size, summary_energy, max_fraction, doc_cut)
-        return cls(HostIndex.build(ds, cfg))
+        return cls(HostIndex.build(ds, cfg))._apply_knn_args(nknn, knn_path)
 
     def save(self, path: str) -> None:
         self._host.save(path + ".index.seismic")

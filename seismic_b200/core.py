@@ -159,6 +159,23 @@ class HostIndex:
         N.check(N.lib().shost_index_convert_dotvbyte(self._h, C.byref(out)))
         return HostIndex(out.value)
 
+    # -- kNN graph (reference Knn{n_vecs, dim, neighbours}, src/inverted_index.rs:430-434)
+    def set_knn(self, neighbours: Optional[np.ndarray]) -> None:
+        """Attach (or, with None, drop) a kNN graph: uint64 [len, dim] document ids, PAD_ID = no neighbour."""
+        if neighbours is None:
+            self._knn = None
+            self._view.knn_dim, self._view.knn_neighbours = 0, None
+            return
+        nb = np.ascontiguousarray(neighbours, dtype=np.uint64)
+        if nb.ndim != 2 or nb.shape[0] != self.len or nb.shape[1] == 0:
+            raise ValueError("kNN graph must have shape [len, dim > 0]")
+        self._knn = nb  # keeps the buffer the view points to alive
+        self._view.knn_dim, self._view.knn_neighbours = nb.shape[1], N.ptr(nb)
+
+    @property
+    def knn(self) -> Optional[np.ndarray]:
+        return getattr(self, "_knn", None)
+
     @property
     def value_kind(self) -> int:
         return int(self._view.value_kind)
@@ -195,6 +212,28 @@ class HostIndex:
         n = C.c_uint32()
         N.check(N.lib().shost_index_get_doc(self._h, i, N.ptr(comps), N.ptr(vals), cap, C.byref(n)))
         return comps[: n.value].copy(), vals[: n.value].copy()
+
+    def forward_csr(self, lo: int = 0, hi: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Documents [lo, hi) of the forward index as CSR queries: (offsets u64, components u32, values f32) — the
+        vectors `Knn::new` searches the index with (src/inverted_index.rs:463-470).  Plain encodings only."""
+        v = self._view
+        hi = self.len if hi is None else hi
+        if v.value_kind == N.VAL_DOTVBYTE:
+            raise NotImplementedError("forward_csr: DotVByte forward index")
+        fo = N.np_view(v.fwd_offsets, self.len + 1, np.uint64)
+        a, b = int(fo[lo]), int(fo[hi])
+        comps = N.np_view(v.fwd_comps, int(fo[-1]), np.uint16 if v.comp_bits == 16 else np.uint32)[a:b].astype(np.uint32)
+        kind, total = int(v.value_kind), int(fo[-1])
+        if kind == N.VAL_F16:
+            vals = N.np_view(v.fwd_values, total, np.float16)[a:b].astype(np.float32)
+        elif kind == N.VAL_BF16:
+            vals = (N.np_view(v.fwd_values, total, np.uint16)[a:b].astype(np.uint32) << 16).view(np.float32)
+        elif kind == N.VAL_F32:
+            vals = N.np_view(v.fwd_values, total, np.float32)[a:b].copy()
+        else:
+            code = N.np_view(v.fwd_values, total, np.uint8 if kind == N.VAL_FIXEDU8 else np.uint16)[a:b]
+            vals = code.astype(np.float32) * np.float32(v.value_scale)
+        return (fo[lo:hi + 1] - fo[lo]).astype(np.uint64), comps, vals
 
     # numpy views of the logical arrays (tests, tools)
     def arrays(self) -> dict:
@@ -251,6 +290,16 @@ class GpuIndex:
 
     def set_option(self, name: str, value: int) -> None:
         N.check(N.lib().sgpu_index_set_option(self._h, name.encode(), int(value)))
+
+    def set_knn(self, neighbours: Optional[np.ndarray]) -> None:
+        """(Re)upload the kNN graph used by n_knn > 0 searches: uint64 [len, dim] document ids; None drops it."""
+        if neighbours is None:
+            N.check(N.lib().sgpu_index_set_knn(self._h, None, 0))
+            return
+        nb = np.ascontiguousarray(neighbours, dtype=np.uint64)
+        if nb.ndim != 2 or nb.shape[0] != self.len:
+            raise ValueError("kNN graph must have shape [len, dim]")
+        N.check(N.lib().sgpu_index_set_knn(self._h, N.ptr(nb), nb.shape[1]))
 
     @staticmethod
     def _params(k, query_cut, heap_factor, n_knn, first_sorted) -> N.SearchParams:

@@ -63,6 +63,9 @@ struct DevIndex {
     uint32_t vbyte;   // 1: DotVByte byte stream (4-byte units), u16 components
     uint32_t value_kind;  // SGPU_VAL_* of the records
     float value_scale;
+    const uint64_t* knn_posts;  // [n_docs * knn_dim] neighbours as postings (record start << 16 | padded nnz), ~0 = none
+    uint32_t knn_dim;
+    uint32_t rec_chunk_units;   // units of rec_start per 8-component chunk (plain layouts)
 };
 
 struct Batch {
@@ -370,6 +373,24 @@ __global__ void k_finish(const uint32_t* rec_start, uint64_t n_docs, const uint3
         else hi = mid;
     }
     out_ids[i] = lo - 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_knn_posts: neighbour document ids -> postings of the record image (Knn::refine calls range_from_id per
+// neighbour, src/inverted_index.rs:584; here that is done once per graph).  The nnz field is the record's chunk
+// count * 8 (padding pairs are (0, +0.0) and leave every partial sum bit-identical).
+// ------------------------------------------------------------------------------------------
+__global__ void k_knn_posts(const uint64_t* __restrict__ ids, uint64_t n, const uint32_t* __restrict__ rec_start,
+                            uint64_t n_docs, uint32_t chunk_units, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t d = ids[i];
+    uint64_t post = ~0ull;
+    if (d < n_docs) {
+        const uint32_t r0 = rec_start[d], nch = (rec_start[d + 1] - r0) / chunk_units;
+        if (nch > 0) post = ((uint64_t)r0 << 16) | (uint64_t)min(nch * 8u, 65535u);
+    }
+    out[i] = post;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -62,6 +62,7 @@ struct SearchArgs {
     uint32_t k;
     float heap_factor;
     int first_sorted;
+    uint32_t n_knn;            // Knn::refine: neighbours per result document (0 = off; <= ix.knn_dim)
     uint32_t wave_docs;        // soft cap of documents per wave
     uint32_t first_wave_docs;  // soft cap for the first wave of a query (heap still empty)
     uint32_t buf_docs;         // capacity of the wave buffers (>= wave caps); larger blocks are split
@@ -640,10 +641,12 @@ struct RegHeap {
         }
     }
     // push up to 32 items, one per lane; items already retained (same key) are ignored
-    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane) {
+    // `distinct`: the keys of one call are known to differ (always true inside one posting list)
+    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane,
+                                          bool distinct = true) {
         {
             const uint32_t m0 = __ballot_sync(0xffffffffu, have && (n < k || better(sc, ky, theta, wkey)));
-            if (__popc(m0) > 2) {
+            if (distinct && __popc(m0) > 2) {
                 merge32(m0, sc, ky, lane);
                 return;
             }
@@ -669,6 +672,9 @@ struct RegHeap {
                 wkey = __shfl_sync(0xffffffffu, key, k - 1);
             }
         }
+    }
+    __device__ __forceinline__ void store_keys(uint32_t* dst, uint32_t lane) const {
+        if (lane < n) dst[lane] = key;
     }
     __device__ __forceinline__ void write_sorted(uint32_t lane, uint32_t* out_keys, float* out_scores) const {
         for (uint32_t i = lane; i < k; i += 32) {
@@ -705,7 +711,7 @@ struct SmemHeap {
         }
         theta = s, wkey = key, widx = idx;
     }
-    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane) {
+    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane, bool = true) {
         for (;;) {
             const bool fl = n == k;
             const bool c = have && (!fl || better(sc, ky, theta, wkey));
@@ -724,6 +730,9 @@ struct SmemHeap {
             __syncwarp();
             if (n == k) find_worst(lane);
         }
+    }
+    __device__ __forceinline__ void store_keys(uint32_t* dst, uint32_t lane) const {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = hk[i];
     }
     __device__ __forceinline__ void write_sorted(uint32_t lane, uint32_t* out_keys, float* out_scores) const {
         for (uint32_t i = lane; i < n; i += 32) {
@@ -843,7 +852,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             for (int j = 0; j < D; ++j) {
                 const float s = group_reduce(acc[j]);
                 const uint32_t d = dbase + j * GROUPS + grp;
-                if (lane8 == 0 && d < n) {
+                if (lane8 == 0 && d < n && (post[j] & 0xffffu)) {  // nnz 0: an absent kNN neighbour
                     scores[d] = s;
                     if constexpr (!is_vbyte<R>::value) st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
                     // theta only grows: a document that cannot enter the heap as of the wave start never will
@@ -853,12 +862,12 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         }
     };
     // warp 0: offer the surviving documents of wave slots [c0, c1) to the heap
-    auto push_range = [&](uint32_t c0, uint32_t c1) {
-            for (uint32_t base = c0 & ~31u; base < c1; base += 32) {
-                const uint32_t i = base + lane;
-                const bool have = i >= c0 && i < c1 && ((surv[base >> 5] >> lane) & 1u);
-                heap.offer(have, have ? scores[i] : 0.f, have ? (uint32_t)(docs[i] >> 16) : 0u, lane);
-            }
+    auto push_range = [&](uint32_t c0, uint32_t c1, bool distinct = true) {
+        for (uint32_t base = c0 & ~31u; base < c1; base += 32) {
+            const uint32_t i = base + lane;
+            const bool have = i >= c0 && i < c1 && ((surv[base >> 5] >> lane) & 1u);
+            heap.offer(have, have ? scores[i] : 0.f, have ? (uint32_t)(docs[i] >> 16) : 0u, lane, distinct);
+        }
     };
 
     for (;;) {
@@ -1043,6 +1052,49 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 }
                 __syncthreads();
                 lap(4);
+            }
+        }
+        if (a.n_knn > 0 && nt > 0) {
+            // ---------------- Knn::refine (src/inverted_index.rs:551-593): the first n_knn graph neighbours of every
+            // document retained so far are scored and pushed.  The reference walks a sorted snapshot of the heap and
+            // skips visited documents; the result is the k best of (heap U neighbours) in any order, and a document
+            // seen before is either still retained (offer() ignores it) or can no longer enter (see the header).
+            uint32_t* snap = cand_end;  // the four candidate arrays are contiguous: 4 * cand_cap >= k entries (host)
+            if (warp == 0) {
+                heap.store_keys(snap, lane);
+                if (lane == 0) s_wave_cnt = heap.n;
+            }
+            __syncthreads();
+            const uint32_t n_snap = s_wave_cnt;
+            for (uint32_t e = tid; e < n_snap; e += T) {  // id_from_range: key (record start) -> document
+                const uint32_t key = snap[e];
+                uint64_t lo = 0, hi = a.ix.n_docs + 1;
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (__ldg(a.ix.rec_start + mid) <= key) lo = mid + 1;
+                    else hi = mid;
+                }
+                snap[e] = (uint32_t)(lo - 1);
+            }
+            __syncthreads();
+            const uint32_t total = n_snap * a.n_knn;
+            for (uint32_t base = 0; base < total; base += a.buf_docs) {
+                const uint32_t part = min(a.buf_docs, total - base);
+                for (uint32_t i = tid; i < part; i += T) {
+                    const uint32_t c = base + i;
+                    const uint64_t pst = a.ix.knn_posts[(uint64_t)snap[c / a.n_knn] * a.ix.knn_dim + c % a.n_knn];
+                    docs[i] = pst == ~0ull ? 0ull : pst;
+                }
+                for (uint32_t i = tid; i < (part + 31) >> 5; i += T) surv[i] = 0u;
+                __syncthreads();
+                score_wave(part, 0);
+                __syncthreads();
+                if (warp == 0) {
+                    st_docs += part;
+                    push_range(0, part, false);  // two retained documents may share a neighbour
+                    if (lane == 0) s_full = heap.full(), s_theta = heap.theta, s_wkey = heap.wkey;
+                }
+                __syncthreads();
             }
         }
         // ---------------- results: best first, padded

@@ -79,7 +79,7 @@ struct SgpuIndex {
     cudaStream_t own_stream = nullptr;  // the library's private stream
     cudaEvent_t ev[8] = {};
     // image
-    DevBuf lists, postings, blk_post_off, blk_min, blk_quant, sc_comp, sc_run_off, ent_blk, ent_code, fwd, rec_start;
+    DevBuf lists, postings, blk_post_off, blk_min, blk_quant, sc_comp, sc_run_off, ent_blk, ent_code, fwd, rec_start, knn_posts;
     sgpu::DevIndex ix{};
     uint64_t image_bytes = 0;
     uint32_t max_blocks = 0;      // largest number of blocks of any list
@@ -115,6 +115,34 @@ int upload(DevBuf& dst, const T* src, size_t n, cudaStream_t st, uint64_t* total
     CK(dst.ensure(n * sizeof(T)));
     if (n) CK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
     *total += n * sizeof(T);
+    return SGPU_OK;
+}
+
+// Upload a kNN graph (host array of doc ids) and turn it into postings of the record image.
+int set_knn_impl(SgpuIndex* ix, const uint64_t* neighbours, uint32_t knn_dim) {
+    if (!ix) return SGPU_EINVAL;
+    CK(cudaSetDevice(ix->device));
+    if (!neighbours || knn_dim == 0) {
+        ix->ix.knn_posts = nullptr;
+        ix->ix.knn_dim = 0;
+        return SGPU_OK;
+    }
+    if (ix->ix.vbyte) {
+        shost::set_error("kNN graphs are not available for DotVByte indexes (as in the reference)");
+        return SGPU_EUNSUPPORTED;
+    }
+    const uint64_t n = ix->ix.n_docs * (uint64_t)knn_dim;
+    cudaStream_t st = ix->stream;
+    DevBuf d_ids;
+    CK(d_ids.ensure(n * 8));
+    CK(ix->knn_posts.ensure(n * 8));
+    CK(cudaMemcpyAsync(d_ids.p, neighbours, n * 8, cudaMemcpyHostToDevice, st));
+    k_knn_posts<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ids.as<uint64_t>(), n, ix->ix.rec_start, ix->ix.n_docs,
+                                                            ix->ix.rec_chunk_units, ix->knn_posts.as<uint64_t>());
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ix->ix.knn_posts = ix->knn_posts.as<uint64_t>();
+    ix->ix.knn_dim = knn_dim;
     return SGPU_OK;
 }
 
@@ -301,6 +329,11 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     d.vbyte = vbyte ? 1u : 0u;
     d.value_kind = kind;
     d.value_scale = v->value_scale;
+    d.knn_posts = nullptr;
+    d.knn_dim = 0;
+    d.rec_chunk_units = vbyte ? 1u : chunk_units;
+    if (v->knn_neighbours && v->knn_dim)
+        if (int rc = set_knn_impl(ix.get(), v->knn_neighbours, v->knn_dim)) return rc;
     *out = ix.release();
     return SGPU_OK;
 }
@@ -320,9 +353,9 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         shost::set_error("k > 1024 is not supported");
         return SGPU_EUNSUPPORTED;
     }
-    if (p->n_knn != 0) {
-        shost::set_error("n_knn > 0 (Knn::refine) is not implemented in this release");
-        return SGPU_EUNSUPPORTED;
+    if (p->n_knn != 0 && (!ix->ix.knn_posts || ix->ix.knn_dim == 0)) {
+        shost::set_error("n_knn > 0 needs a kNN graph (sgpu_index_set_knn / SgpuIndexView.knn_neighbours)");
+        return SGPU_EINVAL;
     }
     if (dq->n_queries >= (1ull << 31)) {
         shost::set_error("too many queries in one batch");
@@ -381,6 +414,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ad.k = k;
     ad.heap_factor = p->heap_factor;
     ad.first_sorted = p->first_sorted ? 1 : 0;
+    ad.n_knn = std::min(p->n_knn, ix->ix.knn_dim);
     ad.wave_docs = std::max(1u, ix->wave_docs);
     ad.first_wave_docs = std::max(1u, ix->first_wave_docs);
     ad.buf_docs = std::max(ad.wave_docs, ad.first_wave_docs);
@@ -462,6 +496,10 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         hq_ok = occ >= 1;
         hq_ctas = occ * ix->n_sm;
         ctas_per_sm = (uint32_t)occ;
+    }
+    if (ad.n_knn > 0 && ((hq_ok && k > 4 * ah.cand_cap) || (dense_ok && k > 4 * ad.cand_cap))) {
+        shost::set_error("n_knn > 0: k exceeds the snapshot buffer of the search kernel");
+        return SGPU_EUNSUPPORTED;
     }
     if (!hq_ok && !dense_ok) {
         shost::set_error("neither the compact-query nor the dense-query kernel fits this index in shared memory");
@@ -591,6 +629,10 @@ int sgpu_index_set_stream(SgpuIndex* ix, void* cuda_stream) {
     if (!ix) return SGPU_EINVAL;
     ix->stream = cuda_stream ? (cudaStream_t)cuda_stream : ix->own_stream;
     return SGPU_OK;
+}
+
+int sgpu_index_set_knn(SgpuIndex* ix, const uint64_t* neighbours, uint32_t knn_dim) {
+    return set_knn_impl(ix, neighbours, knn_dim);
 }
 
 int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {

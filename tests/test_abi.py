@@ -40,7 +40,7 @@ def test_version_and_defaults(native):
 
 def test_struct_layouts_match_header(native):
     # sizes the C compiler gives these structs (x86-64 SysV): guards against binding drift
-    assert ctypes.sizeof(native.IndexView) == 32 + 16 * 8
+    assert ctypes.sizeof(native.IndexView) == 32 + 17 * 8
     assert ctypes.sizeof(native.QueryBatch) == 32
     assert ctypes.sizeof(native.SearchParams) == 20
     assert ctypes.sizeof(native.SearchStats) == 28 + 4 + 32 + 48 + 16

@@ -118,14 +118,13 @@ def test_dataset_growable():
     assert (idx.len, idx.dim, idx.nnz) == (2, 3, 4)
 
 
-def test_knn_is_explicitly_unsupported(toy_jsonl):
+def test_knn_errors_without_a_graph(toy_jsonl):
     idx = seismic.SeismicIndex.build(str(toy_jsonl / "documents.jsonl"))
-    with pytest.raises(NotImplementedError):
-        idx.build_knn(5)
-    with pytest.raises(ValueError):
+    assert idx.knn_len == 0
+    with pytest.raises(ValueError):  # PyValueError in the reference (src/pylib/mod.rs:260-264)
         idx.save_knn("/tmp/x")
-    with pytest.raises(NotImplementedError):
-        seismic.SeismicIndex.build(str(toy_jsonl / "documents.jsonl"), nknn=5)
+    with pytest.raises(OSError):
+        seismic.SeismicIndex.build(str(toy_jsonl / "documents.jsonl"), knn_path="/nonexistent/g.knn.seismic")
 
 
 # ------------------------------------------------------------------------------------------------ GPU
