@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
 
     __shared__ uint32_t s_q;
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
-    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0;
+    __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0, s_snap_n;
     __shared__ float s_theta;
     __shared__ uint32_t s_full, s_wkey;
     // phase clocks (thread 0 only, kept in shared memory to spare registers):
@@ -1060,12 +1060,13 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             // skips visited documents; the result is the k best of (heap U neighbours) in any order, and a document
             // seen before is either still retained (offer() ignores it) or can no longer enter (see the header).
             uint32_t* snap = cand_end;  // the four candidate arrays are contiguous: 4 * cand_cap >= k entries (host)
+            __syncthreads();  // a selection pass that found nothing leaves the list loop without a barrier
             if (warp == 0) {
                 heap.store_keys(snap, lane);
-                if (lane == 0) s_wave_cnt = heap.n;
+                if (lane == 0) s_snap_n = heap.n;
             }
             __syncthreads();
-            const uint32_t n_snap = s_wave_cnt;
+            const uint32_t n_snap = s_snap_n;
             for (uint32_t e = tid; e < n_snap; e += T) {  // id_from_range: key (record start) -> document
                 const uint32_t key = snap[e];
                 uint64_t lo = 0, hi = a.ix.n_docs + 1;

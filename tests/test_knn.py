@@ -161,3 +161,21 @@ def test_gpu_build_knn_matches_oracle_graph(oracle_mod):
     ref = oracle_mod.batch_search(host.view, q.offsets, q.comps, q.values, 10, 2, 0.9, n_knn=5, first_sorted=True)
     got = idx.gpu.batch_search(q.offsets, q.comps, q.values, 10, 2, 0.9, n_knn=5, first_sorted=True)
     assert (got[0] == ref[0]).all() and np.array_equal(got[1], ref[1])
+
+
+@pytest.mark.gpu
+def test_gpu_refine_many_queries_per_cta(oracle_mod):
+    """Regression: with several queries per CTA and query_cut 1, a selection pass that finds nothing leaves the list
+    loop without a barrier; the refine must not reuse shared state a slower warp is still reading (found with
+    compute-sanitizer --tool racecheck)."""
+    cfg = Dataset.synth_config(30000, dim=2000)
+    index = HostIndex.build(Dataset.synth_documents(cfg), n_postings=600, centroid_fraction=0.2)
+    q = Dataset.synth_queries(cfg, 6000)
+    rng = np.random.default_rng(3)
+    index.set_knn(rng.integers(0, index.len, size=(index.len, 10), dtype=np.uint64))
+    gpu = GpuIndex(index, 0)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 1, 0.9, n_knn=10, first_sorted=True)
+    for _ in range(3):
+        got = gpu.batch_search(q.offsets, q.comps, q.values, 10, 1, 0.9, n_knn=10, first_sorted=True)
+        assert (got[2] == ref[2]).all() and (got[0] == ref[0]).all()
+        assert np.array_equal(got[1].view(np.uint32), ref[1].view(np.uint32))
