@@ -117,7 +117,7 @@ typedef struct SgpuSearchParams {
     uint32_t k;
     uint32_t query_cut;
     float heap_factor;
-    uint32_t n_knn;        /* > 0: Knn::refine with min(n_knn, knn_dim) neighbours (needs a graph) */
+    uint32_t n_knn;        /* > 0: Knn::refine with min(n_knn, knn_dim) neighbours; ignored without a graph */
     int32_t first_sorted;  /* Python default True (src/pylib/mod.rs:497-498), CLI default false */
 } SgpuSearchParams;
 

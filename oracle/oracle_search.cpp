@@ -404,7 +404,7 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
             }
         }
     }
-    if (p.n_knn > 0) {
+    if (p.n_knn > 0 && v.knn_neighbours && v.knn_dim) {  // `if n_knn > 0 && let Some(knn)`, src/inverted_index.rs:215-217
         // Knn::refine (src/inverted_index.rs:551-593): snapshot of the heap, best first; for each retained document
         // its first min(dim, n_knn) graph neighbours; unvisited ones are scored and pushed.
         const uint32_t n_knn = std::min<uint32_t>(v.knn_dim, p.n_knn);
@@ -448,8 +448,7 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
 
 int validate(const SgpuIndexView* v, const SgpuQueryBatch* qb, const SgpuSearchParams* p) {
     if (!v || !qb || !p || p->k == 0) return SGPU_EINVAL;
-    if (p->n_knn != 0 && (!v->knn_neighbours || v->knn_dim == 0)) return SGPU_EINVAL;
-    if (p->n_knn != 0 && v->value_kind == SGPU_VAL_DOTVBYTE) return SGPU_EUNSUPPORTED;  // no kNN on DotVByte
+    if (p->n_knn != 0 && v->knn_neighbours && v->value_kind == SGPU_VAL_DOTVBYTE) return SGPU_EUNSUPPORTED;  // no kNN on DotVByte
     if (v->value_kind == SGPU_VAL_DOTVBYTE && (v->comp_bits != 16 || !v->fwd_nnz)) return SGPU_EUNSUPPORTED;
     for (uint64_t qi = 0; qi < qb->n_queries; ++qi)
         for (uint64_t i = qb->offsets[qi]; i < qb->offsets[qi + 1]; ++i) {

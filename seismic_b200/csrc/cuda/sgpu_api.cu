@@ -353,10 +353,6 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         shost::set_error("k > 1024 is not supported");
         return SGPU_EUNSUPPORTED;
     }
-    if (p->n_knn != 0 && (!ix->ix.knn_posts || ix->ix.knn_dim == 0)) {
-        shost::set_error("n_knn > 0 needs a kNN graph (sgpu_index_set_knn / SgpuIndexView.knn_neighbours)");
-        return SGPU_EINVAL;
-    }
     if (dq->n_queries >= (1ull << 31)) {
         shost::set_error("too many queries in one batch");
         return SGPU_EINVAL;
@@ -414,7 +410,8 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ad.k = k;
     ad.heap_factor = p->heap_factor;
     ad.first_sorted = p->first_sorted ? 1 : 0;
-    ad.n_knn = std::min(p->n_knn, ix->ix.knn_dim);
+    // no graph attached: the reference skips the refine (`if n_knn > 0 && let Some(knn)`, src/inverted_index.rs:215-217)
+    ad.n_knn = ix->ix.knn_posts ? std::min(p->n_knn, ix->ix.knn_dim) : 0u;
     ad.wave_docs = std::max(1u, ix->wave_docs);
     ad.first_wave_docs = std::max(1u, ix->first_wave_docs);
     ad.buf_docs = std::max(ad.wave_docs, ad.first_wave_docs);

@@ -236,8 +236,8 @@ def test_empty_batch_and_errors(synth_pruned, gpu_pruned):
         gpu_pruned.batch_search(off, np.array([3, index.dim], np.uint32), np.ones(2, np.float32), 10, 3, 0.8)
     with pytest.raises(ValueError):
         gpu_pruned.batch_search(off, np.array([3, 9], np.uint32), np.ones(2, np.float32), 0, 3, 0.8)
-    with pytest.raises(ValueError):  # n_knn > 0 without a kNN graph
-        gpu_pruned.batch_search(off, np.array([3, 9], np.uint32), np.ones(2, np.float32), 10, 3, 0.8, n_knn=5)
+    # n_knn > 0 without a kNN graph is not an error: the reference skips the refine (src/inverted_index.rs:215-217)
+    gpu_pruned.batch_search(off, np.array([3, 9], np.uint32), np.ones(2, np.float32), 10, 3, 0.8, n_knn=5)
     # the index stays usable after an error
     got = gpu_pruned.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8)
     assert got[2].max() == 10

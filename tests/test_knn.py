@@ -32,8 +32,9 @@ def test_refine_known_answer(oracle_mod):
     off, qc, qv = csr([0, 1], [1.0, 1.0])
     ids, scores, counts, _ = oracle_mod.batch_search(index.view, off, qc, qv, 4, 1, 0.8, n_knn=0, first_sorted=True)
     assert counts[0] == 2 and ids[0, :2].tolist() == [0, 2]
-    with pytest.raises(Exception):  # n_knn > 0 without a graph
-        oracle_mod.batch_search(index.view, off, qc, qv, 4, 1, 0.8, n_knn=1, first_sorted=True)
+    # n_knn > 0 without a graph: the refine is skipped (`if n_knn > 0 && let Some(knn)`, src/inverted_index.rs:215-217)
+    ids2, _, counts2, _ = oracle_mod.batch_search(index.view, off, qc, qv, 4, 1, 0.8, n_knn=1, first_sorted=True)
+    assert counts2[0] == 2 and ids2[0, :2].tolist() == [0, 2]
     graph = np.array([[1, 4], [0, PAD], [1, PAD], [PAD, PAD], [PAD, PAD]], dtype=np.uint64)
     index.set_knn(graph)
     ids, scores, counts, st = oracle_mod.batch_search(index.view, off, qc, qv, 4, 1, 0.8, n_knn=1, first_sorted=True)
@@ -119,9 +120,9 @@ def test_gpu_refine_known_answer(oracle_mod):
         ref = oracle_mod.batch_search(index.view, off, qc, qv, k, 1, 0.8, n_knn=n_knn, first_sorted=True)
         got = gpu.batch_search(off, qc, qv, k, 1, 0.8, n_knn=n_knn, first_sorted=True)
         assert (got[2] == ref[2]).all() and (got[0] == ref[0]).all() and np.array_equal(got[1], ref[1]), (k, n_knn)
-    gpu.set_knn(None)
-    with pytest.raises(ValueError):
-        gpu.batch_search(off, qc, qv, 4, 1, 0.8, n_knn=1)
+    gpu.set_knn(None)  # no graph: n_knn is ignored, as in the reference
+    got = gpu.batch_search(off, qc, qv, 4, 1, 0.8, n_knn=1)
+    assert got[2][0] == 2 and got[0][0, :2].tolist() == [0, 2]
 
 
 @pytest.mark.gpu
