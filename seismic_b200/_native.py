@@ -175,6 +175,8 @@ def lib() -> C.CDLL:
         path = LIB_PATH
     handle = C.CDLL(str(path))
     for name, (res, args) in SYMBOLS.items():
+        if override and not hasattr(handle, name):
+            continue  # an older build in an A/B run
         fn = getattr(handle, name)
         fn.restype = res
         fn.argtypes = args

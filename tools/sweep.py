@@ -65,7 +65,9 @@ for cut in [int(x) for x in a.cuts.split(',')]:
                                   "image_GB": round(gpu.device_bytes / 1e9, 2)}), flush=True)
             row = {"query_cut": cut, "heap_factor": hf, "sorted": srt, "recall": round(rec, 4),
                    "qps_kernels": round(a.queries / best["ms_total"] * 1e3), "ms_search": round(best["ms_search"], 3),
-                   "ms_total": round(best["ms_total"], 3), "docs_per_query": round(best["docs_scored"] / a.queries, 1)}
+                   "ms_total": round(best["ms_total"], 3), "docs_per_query": round(best["docs_scored"] / a.queries, 1),
+                   "phase_share": [round(c / max(1, sum(best["phase_cycles"])), 3) for c in best["phase_cycles"]],
+                   "waves_per_query": round(best.get("waves", 0) / a.queries, 1)}
             rows.append(row)
             print(json.dumps(row), flush=True)
 Path("gpurun_out").mkdir(exist_ok=True)
