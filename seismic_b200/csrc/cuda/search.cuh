@@ -193,6 +193,19 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
             a1 = __fadd_rn(a1, __fmul_rn(q[8 + 2 * e + 1], h_hi(v1)));
         }
     }
+    // Eight decoded (component, f32 value) pairs of one lane (DotVByte): all index loads, then all value loads, then the
+    // ordered multiply-add chain.  Misses read vals[0] = +0.0 and add +-0: bit-identical to skipping them (mac_f).
+    __device__ __forceinline__ float dot8f(float acc, const uint32_t (&c)[8], const float (&v)[8]) const {
+        uint32_t idx[8];
+        float q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(idx[e]) : "r"(qidx_s + c[e]));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(q[e]) : "r"(vals_s + idx[e] * 4));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = __fadd_rn(acc, __fmul_rn(q[e], v[e]));
+        return acc;
+    }
     static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return 1024 + (size_t)a.qd_words * 4; }
     __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
 #if SGPU_SKIP_MISS
@@ -565,7 +578,9 @@ __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream
             const uint32_t w0 = __ldg(gw), w1 = __ldg(gw + 1), w2 = __ldg(gw + 2), w3 = __ldg(gw + 3), w4 = __ldg(gw + 4);
             uint64_t lo = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
             uint64_t hi = ((uint64_t)__funnelshift_r(w3, w4, sh) << 32) | __funnelshift_r(w2, w3, sh);
-            float a = acc[j];
+            // decode the chunk first (ALU only), then look all eight components up together
+            uint32_t comp[8];
+            float val[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 if (e) {
@@ -575,12 +590,19 @@ __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream
                     lo = (lo >> s) | (hi << (64 - s));
                     hi >>= s;
                 }
+                comp[e] = c;
                 const uint32_t code = ((e < 4 ? v0 : v1) >> (8 * (e & 3))) & 0xffu;
                 // (float)code exactly, without the conversion pipe: 2^23 + code as float bits, minus 2^23
-                const float val = __fmul_rn(__uint_as_float(0x4b000000u | code) - 8388608.f, scale);
-                a = q.mac_f(a, c, val);
+                val[e] = __fmul_rn(__uint_as_float(0x4b000000u | code) - 8388608.f, scale);
             }
-            acc[j] = a;
+            if constexpr (Q::HAS_DOT8) {
+                acc[j] = q.dot8f(acc[j], comp, val);
+            } else {
+                float a = acc[j];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a = q.mac_f(a, comp[e], val[e]);
+                acc[j] = a;
+            }
         }
     }
 }

@@ -96,6 +96,7 @@ if a.dotvbyte:
                "qps_kernels": round(a.queries / best["ms_total"] * 1e3), "ms_search": round(best["ms_search"], 3),
                "parity_mismatch_first_2000": mism, "scores_equal": bool(np.array_equal(sc[:n], ref[1])),
                "algorithmic_GBps_k_search": round(alg / best["ms_search"] / 1e6, 1), "fwd_bytes_read": best["fwd_bytes"],
-               "cpu_all_threads_qps": round(a.queries / all_ref[3]["seconds"]), "image_GB": round(g.device_bytes / 1e9, 2)}
+               "cpu_all_threads_qps": round(a.queries / all_ref[3]["seconds"]), "image_GB": round(g.device_bytes / 1e9, 2),
+               "phase_share": [round(c / max(1, sum(best["phase_cycles"])), 3) for c in best["phase_cycles"]]}
         print(json.dumps(row), flush=True)
         Path("gpurun_out/sweep_dotvbyte_%d.json" % a.docs).write_text(json.dumps(row, indent=1))
