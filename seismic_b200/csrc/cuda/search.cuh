@@ -886,8 +886,12 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     // warp 0: offer the surviving documents of wave slots [c0, c1) to the heap
     auto push_range = [&](uint32_t c0, uint32_t c1, bool distinct = true) {
         for (uint32_t base = c0 & ~31u; base < c1; base += 32) {
+            uint32_t w = surv[base >> 5];  // warp-uniform
+            if (base < c0) w &= 0xffffffffu << (c0 - base);
+            if (c1 - base < 32) w &= (1u << (c1 - base)) - 1u;
+            if (!w) continue;  // no survivor of this range in these 32 slots (a block usually spans two such groups)
             const uint32_t i = base + lane;
-            const bool have = i >= c0 && i < c1 && ((surv[base >> 5] >> lane) & 1u);
+            const bool have = (w >> lane) & 1u;
             heap.offer(have, have ? scores[i] : 0.f, have ? (uint32_t)(docs[i] >> 16) : 0u, lane, distinct);
         }
     };
