@@ -1,0 +1,139 @@
+"""A second, independent restatement of the reference's search path — pure Python / numpy float32, written from the
+reference sources (not from oracle/oracle_search.cpp) and used only to cross-check the C++ oracle on small random
+indexes (tests/test_oracle_crosscheck.py).  Slow by design.
+
+  InvertedIndexBase::search        /root/reference/src/inverted_index.rs:153-234
+  QuantizedSummary::distances      src/quantized_summary.rs:64-160
+  PostingList::search / sort_and_search / evaluate_posting_block   src/posting_list.rs:115-215
+  KHeap                            src/utils.rs:12-66
+  Knn::refine                      src/inverted_index.rs:551-593
+The choices the reference leaves to its absent dependencies are the oracle's: score = 8 partial sums
+(element i -> partial (i / 8) % 8, mul then add in f32) reduced as ((p0+p4)+(p2+p6))+((p1+p5)+(p3+p7)); better = higher
+score, then smaller forward offset; equal query values: earlier position; equal estimates: smaller block id."""
+import numpy as np
+
+F = np.float32
+PAD = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _key(x):  # f32::total_cmp as an integer key
+    b = int(np.float32(x).view(np.uint32))
+    return (~b & 0xFFFFFFFF) if b & 0x80000000 else (b | 0x80000000)
+
+
+class KHeap:
+    """Bounded set of the k best items; push replaces the worst only if the new item is strictly better."""
+
+    def __init__(self, k):
+        self.k, self.items = k, []  # items: (score f32, start)
+
+    @staticmethod
+    def better(a, b):
+        return a[0] > b[0] or (a[0] == b[0] and a[1] < b[1])
+
+    def worst(self):
+        w = self.items[0]
+        for it in self.items[1:]:
+            if self.better(w, it):
+                w = it
+        return w
+
+    def push(self, item):
+        if len(self.items) < self.k:
+            self.items.append(item)
+        else:
+            w = self.worst()
+            if self.better(item, w):
+                self.items[self.items.index(w)] = item
+
+    def sorted(self):
+        out = list(self.items)
+        for i in range(1, len(out)):  # insertion sort with the same order
+            j = i
+            while j > 0 and self.better(out[j], out[j - 1]):
+                out[j], out[j - 1] = out[j - 1], out[j]
+                j -= 1
+        return out
+
+
+class PyIndex:
+    def __init__(self, host):
+        a = host.arrays()
+        self.a = a
+        self.n_docs, self.dim = host.len, host.dim
+        self.off, self.comps, self.vals = host.forward_csr()
+        self.fo = a["fwd_offsets"].astype(np.int64)
+        self.knn = host.knn
+
+    def doc_score(self, q, start, ln):
+        p = [F(0)] * 8
+        for i in range(ln):
+            c = int(self.comps[start + i])
+            lane = (i // 8) % 8
+            p[lane] = F(p[lane] + F(q[c] * self.vals[start + i]))
+        return F(F(F(p[0] + p[4]) + F(p[2] + p[6])) + F(F(p[1] + p[5]) + F(p[3] + p[7])))
+
+    def distances(self, l, qc, qv):
+        a = self.a
+        b0, b1 = int(a["list_blk_start"][l]), int(a["list_blk_start"][l + 1])
+        B = b1 - b0
+        est = np.zeros(B, dtype=F)
+        mins, quants = a["blk_min"][b0:b1], a["blk_quant"][b0:b1]
+        s0, s1 = int(a["list_sc_start"][l]), int(a["list_sc_start"][l + 1])
+        sc = a["sc_comp"][s0:s1]
+        run = a["sc_run_off"][s0 + l: s1 + l + 1]
+        e0 = int(a["list_ent_start"][l])
+        eb, ec = a["ent_blk"][e0:], a["ent_code"][e0:]
+        for j in range(len(qc)):
+            if j > 0 and qc[j] == qc[j - 1]:
+                continue
+            i = int(np.searchsorted(sc, qc[j]))
+            if i == len(sc) or sc[i] != qc[j]:
+                continue
+            for e in range(int(run[i]), int(run[i + 1])):
+                s = int(eb[e])
+                deq = F(F(F(ec[e]) * quants[s]) + mins[s])
+                est[s] = F(est[s] + F(deq * F(qv[j])))
+        return est
+
+    def search(self, qc, qv, k, query_cut, heap_factor, n_knn=0, first_sorted=True):
+        a = self.a
+        q = np.zeros(self.dim, dtype=F)
+        for c, v in zip(qc, qv):
+            q[int(c)] = F(v)
+        heap, visited = KHeap(k), set()
+        terms = sorted(range(len(qc)), key=lambda i: (-_key(qv[i]), i))[: min(query_cut, len(qc))]
+        evaluated = 0
+        for t, ti in enumerate(terms):
+            l = int(qc[ti])
+            est = self.distances(l, qc, qv)
+            B = len(est)
+            order = list(range(B))
+            if t == 0 and first_sorted:
+                order.sort(key=lambda b: (-_key(est[b]), b))
+            boff = a["blk_post_off"][int(a["list_blk_start"][l]) + l:]
+            posts = a["postings"][int(a["list_post_start"][l]):]
+            for b in order:
+                if len(heap.items) == k and est[b] < F(F(heap_factor) * heap.worst()[0]):
+                    continue
+                evaluated += 1
+                for i in range(int(boff[b]), int(boff[b + 1])):
+                    start, ln = int(posts[i]) >> 16, int(posts[i]) & 0xFFFF
+                    if start not in visited:
+                        visited.add(start)
+                        heap.push((self.doc_score(q, start, ln), start))
+        if n_knn > 0 and self.knn is not None:
+            dim_knn = self.knn.shape[1]
+            for _, start in heap.sorted():
+                d = int(np.searchsorted(self.fo, start, side="right")) - 1
+                for i in range(min(dim_knn, n_knn)):
+                    nb = self.knn[d, i]
+                    if nb == PAD:
+                        continue
+                    s2, e2 = int(self.fo[int(nb)]), int(self.fo[int(nb) + 1])
+                    if e2 > s2 and s2 not in visited:
+                        visited.add(s2)
+                        heap.push((self.doc_score(q, s2, e2 - s2), s2))
+        res = heap.sorted()
+        ids = [int(np.searchsorted(self.fo, s, side="right")) - 1 for _, s in res]
+        return ids, [float(s) for s, _ in res], evaluated

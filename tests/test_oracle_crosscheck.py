@@ -1,0 +1,58 @@
+"""The C++ oracle against an independent pure-Python restatement of the reference algorithm (tests/py_reference.py)
+on small random indexes: identical ids, bit-identical f32 scores, identical number of evaluated blocks.  Two
+restatements written separately from the Rust sources agreeing on every discrete decision is the strongest pin this
+repository can put on the oracle beyond the reference's own known-answer tests (no Rust toolchain here)."""
+import numpy as np
+import pytest
+
+from seismic_b200 import Dataset, HostIndex
+from py_reference import PyIndex, PAD
+
+
+def random_index(seed, n_docs=300, dim=60, **build):
+    rng = np.random.default_rng(seed)
+    comps, vals = [], []
+    for _ in range(n_docs):
+        nnz = int(rng.integers(0, 14))  # empty documents included
+        c = np.sort(rng.choice(dim, size=nnz, replace=False)).astype(np.uint32)
+        comps.append(c)
+        vals.append(rng.choice([0.25, 0.5, 1.0, 1.5, 2.0, 3.0], size=nnz).astype(np.float32) if seed % 2 else
+                    rng.random(nnz, dtype=np.float32) * 3)
+    return HostIndex.build(Dataset.from_lists(comps, vals, dim=dim), **build), rng
+
+
+@pytest.mark.parametrize("seed,build", [
+    (1, dict(n_postings=40, centroid_fraction=0.2)),       # quantised values: exact score ties everywhere
+    (2, dict(n_postings=40, centroid_fraction=0.2)),
+    (3, dict(n_postings=8, centroid_fraction=0.5, max_fraction=2.0, summary_energy=0.3)),   # heavy pruning
+    (4, dict(n_postings=100, centroid_fraction=0.05, min_cluster_size=1, summary_energy=0.9)),
+])
+@pytest.mark.parametrize("k,cut,hf,srt,n_knn", [
+    (5, 2, 0.8, True, 0), (5, 2, 0.8, False, 0), (1, 3, 1.0, True, 0), (10, 6, 0.5, True, 0), (3, 1, 1.3, False, 0),
+    (5, 2, 0.9, True, 3), (8, 3, 0.8, False, 5)])
+def test_oracle_matches_python_restatement(oracle_mod, seed, build, k, cut, hf, srt, n_knn):
+    index, rng = random_index(seed, **build)
+    if n_knn:
+        g = rng.integers(0, index.len, size=(index.len, 4), dtype=np.uint64)
+        g[rng.random(g.shape) < 0.2] = PAD
+        index.set_knn(g)
+    py = PyIndex(index)
+    queries = []
+    for _ in range(25):
+        nnz = int(rng.integers(1, 9))
+        c = np.sort(rng.choice(index.dim, size=nnz, replace=False)).astype(np.uint32)
+        v = (rng.choice([0.5, 1.0, 1.0, 2.0], size=nnz) if seed % 2 else rng.random(nnz) * 2).astype(np.float32)
+        queries.append((c, v))
+    off = np.cumsum([0] + [len(c) for c, _ in queries]).astype(np.uint64)
+    qc = np.concatenate([c for c, _ in queries])
+    qv = np.concatenate([v for _, v in queries])
+    ids, scores, counts, st = oracle_mod.batch_search(index.view, off, qc, qv, k, cut, hf, n_knn=n_knn,
+                                                      first_sorted=srt, n_threads=1)
+    evaluated = 0
+    for i, (c, v) in enumerate(queries):
+        p_ids, p_scores, ev = py.search(c, v, k, cut, hf, n_knn=n_knn, first_sorted=srt)
+        evaluated += ev
+        assert counts[i] == len(p_ids), (i, counts[i], p_ids)
+        assert ids[i, : counts[i]].tolist() == p_ids, (i, ids[i], p_ids)
+        assert np.array_equal(scores[i, : counts[i]], np.array(p_scores, dtype=np.float32)), i
+    assert st["blocks_evaluated"] == evaluated
