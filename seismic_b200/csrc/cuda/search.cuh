@@ -43,6 +43,9 @@ constexpr int DENSE_THREADS = 1024;
 #ifndef SGPU_LD256
 #define SGPU_LD256 0
 #endif
+#ifndef SGPU_VB_PRMT
+#define SGPU_VB_PRMT 1  // DotVByte: byte-permute decode of the gaps (0: sequential 64-bit shifts)
+#endif
 #ifndef SGPU_DOT2X
 #define SGPU_DOT2X 1
 #endif
@@ -539,10 +542,25 @@ struct is_vbyte { static constexpr bool value = false; };
 template <>
 struct is_vbyte<RecVB> { static constexpr bool value = true; };
 
+// Table entry for a group of four gap fields with 2-byte flags t (bit i: field i has two bytes): field i starts at
+// byte b_i = i + popcount(t & ((1 << i) - 1)) of the group.  x = selectors of fields 0,1 (low half) and 2,3 (high
+// half) for __byte_perm, y / z = masks clearing the second byte of 1-byte fields, w = 8 * popcount(t) = bit offset of
+// the next group beyond its minimum of four bytes.
+__device__ __forceinline__ uint4 vb_lut_entry(uint32_t t) {
+    uint32_t b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = i + __popc(t & ((1u << i) - 1u));
+    const uint32_t s01 = b[0] | ((b[0] + 1) << 4) | (b[1] << 8) | ((b[1] + 1) << 12);
+    const uint32_t s23 = b[2] | ((b[2] + 1) << 4) | (b[3] << 8) | (min(b[3] + 1, 7u) << 12);
+    const uint32_t m01 = 0x00ff00ffu | ((t & 1u) ? 0x0000ff00u : 0u) | ((t & 2u) ? 0xff000000u : 0u);
+    const uint32_t m23 = 0x00ff00ffu | ((t & 4u) ? 0x0000ff00u : 0u) | ((t & 8u) ? 0xff000000u : 0u);
+    return make_uint4(s01 | (s23 << 16), m01, m23, 8u * __popc(t));
+}
+
 template <int D, class Q>
 __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream, const uint64_t (&post)[D],
                                               uint32_t lane8, uint32_t rounds, const Q& q, float scale,
-                                              float (&acc)[D], uint32_t& bytes) {
+                                              float (&acc)[D], uint32_t& bytes, uint32_t lut_s) {
     const uint8_t* rec[D];
     uint32_t nch[D];
 #pragma unroll
@@ -576,11 +594,41 @@ __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream
             const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)3);
             const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(g) & 3u) * 8;
             const uint32_t w0 = __ldg(gw), w1 = __ldg(gw + 1), w2 = __ldg(gw + 2), w3 = __ldg(gw + 3), w4 = __ldg(gw + 4);
-            uint64_t lo = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
-            uint64_t hi = ((uint64_t)__funnelshift_r(w3, w4, sh) << 32) | __funnelshift_r(w2, w3, sh);
+            // the chunk's gap bytes (7 .. 14 of them) start at byte 0 of the 16-byte window W0..W3
+            const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
+            const uint32_t W2 = __funnelshift_r(w2, w3, sh), W3 = __funnelshift_r(w3, w4, sh);
             // decode the chunk first (ALU only), then look all eight components up together
             uint32_t comp[8];
             float val[8];
+#if SGPU_VB_PRMT
+            // Gaps 1-4 and 5-7 are two groups of (up to) four 1- or 2-byte fields packed in at most 8 bytes each.  A
+            // 16-entry table indexed by the group's 4 control bits gives the byte-permute selectors that spread the
+            // four fields into 16-bit lanes (vb_lut_entry); two PRMT + two AND per group replace seven dependent
+            // 64-bit shift steps.  Group B starts right after group A: 4 + popcount(A's control bits) bytes in.
+            uint4 la, lb;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(la.x), "=r"(la.y), "=r"(la.z), "=r"(la.w) : "r"(lut_s + ((ctrl >> 1) & 0xfu) * 16));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(lb.x), "=r"(lb.y), "=r"(lb.z), "=r"(lb.w) : "r"(lut_s + (ctrl >> 5) * 16));
+            const uint32_t x01 = __byte_perm(W0, W1, la.x) & la.y, x23 = __byte_perm(W0, W1, la.x >> 16) & la.z;
+            const uint32_t B0 = __funnelshift_rc(W1, W2, la.w), B1 = __funnelshift_rc(W2, W3, la.w);
+            const uint32_t y01 = __byte_perm(B0, B1, lb.x) & lb.y, y23 = __byte_perm(B0, B1, lb.x >> 16) & lb.z;
+            comp[0] = c;
+            comp[1] = comp[0] + (x01 & 0xffffu);
+            comp[2] = comp[1] + (x01 >> 16);
+            comp[3] = comp[2] + (x23 & 0xffffu);
+            comp[4] = comp[3] + (x23 >> 16);
+            comp[5] = comp[4] + (y01 & 0xffffu);
+            comp[6] = comp[5] + (y01 >> 16);
+            comp[7] = comp[6] + (y23 & 0xffffu);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // 0x4b0000cc (= 2^23 + code as float bits) in one byte permute; minus 2^23 gives (float)code exactly
+                const uint32_t bits = __byte_perm(e < 4 ? v0 : v1, 0x4b000000u, 0x7650u | (uint32_t)(e & 3));
+                val[e] = __fmul_rn(__uint_as_float(bits) - 8388608.f, scale);
+            }
+#else
+            uint64_t lo = ((uint64_t)W1 << 32) | W0, hi = ((uint64_t)W3 << 32) | W2;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 if (e) {
@@ -595,6 +643,7 @@ __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream
                 // (float)code exactly, without the conversion pipe: 2^23 + code as float bits, minus 2^23
                 val[e] = __fmul_rn(__uint_as_float(0x4b000000u | code) - 8388608.f, scale);
             }
+#endif
             if constexpr (Q::HAS_DOT8) {
                 acc[j] = q.dot8f(acc[j], comp, val);
             } else {
@@ -792,6 +841,9 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     uint32_t* surv = reinterpret_cast<uint32_t*>(p);  // bit d: document d of the wave can still enter the heap
 
     __shared__ uint32_t s_q;
+    __shared__ uint4 s_vb_lut[is_vbyte<R>::value ? 16 : 1];  // DotVByte gap decode (vb_lut_entry); visible after the first barrier of the loop
+    if constexpr (is_vbyte<R>::value)
+        if (threadIdx.x < 16) s_vb_lut[threadIdx.x] = vb_lut_entry(threadIdx.x);
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
     __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0, s_snap_n;
     __shared__ float s_theta;
@@ -867,7 +919,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             float acc[D];
             if constexpr (is_vbyte<R>::value)
                 score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, a.value_scale,
-                                 acc, st_units);
+                                 acc, st_units, (uint32_t)__cvta_generic_to_shared(s_vb_lut));
             else
                 score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, a.value_scale, acc);
 #pragma unroll
