@@ -65,6 +65,9 @@ class PyIndex:
         self.fo = a["fwd_offsets"].astype(np.int64)
         self.knn = host.knn
 
+    def doc_of(self, start):  # id_from_range: the document whose range starts here (the non-empty one)
+        return int(np.searchsorted(self.fo, start, side="right")) - 1
+
     def doc_score(self, q, start, ln):
         p = [F(0)] * 8
         for i in range(ln):
@@ -125,7 +128,7 @@ class PyIndex:
         if n_knn > 0 and self.knn is not None:
             dim_knn = self.knn.shape[1]
             for _, start in heap.sorted():
-                d = int(np.searchsorted(self.fo, start, side="right")) - 1
+                d = self.doc_of(start)
                 for i in range(min(dim_knn, n_knn)):
                     nb = self.knn[d, i]
                     if nb == PAD:
@@ -135,5 +138,43 @@ class PyIndex:
                         visited.add(s2)
                         heap.push((self.doc_score(q, s2, e2 - s2), s2))
         res = heap.sorted()
-        ids = [int(np.searchsorted(self.fo, s, side="right")) - 1 for _, s in res]
+        ids = [self.doc_of(s) for _, s in res]
         return ids, [float(s) for s, _ in res], evaluated
+
+
+def decode_dotvbyte(host):
+    """Independent decoder of the DotVByte forward index (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte;
+    the reference's own byte format lives in vectorium): per document [u16 first component of every chunk of 8 |
+    pad to 4][control byte per chunk | pad to 4][8 u8 codes per chunk][gap bytes: 7 gaps per chunk, 1 byte, or 2
+    bytes little-endian when the control bit of that position is set].  Returns CSR (offsets, components, values)."""
+    from seismic_b200 import _native as N
+    v = host.view
+    n = host.len
+    fo = N.np_view(v.fwd_offsets, n + 1, np.uint64).astype(np.int64)
+    stream = N.np_view(v.fwd_values, int(fo[-1]), np.uint8)
+    nnzs = N.np_view(v.fwd_nnz, n, np.uint16)
+    scale = np.float32(v.value_scale)
+    off, comps, vals = [0], [], []
+    for d in range(n):
+        rec = stream[int(fo[d]):int(fo[d + 1])]
+        ln = int(nnzs[d])
+        nch = (ln + 7) // 8
+        base = rec[: 2 * nch].view(np.uint16)
+        p = (2 * nch + 3) & ~3
+        ctrl = rec[p: p + nch]
+        p += (nch + 3) & ~3
+        codes = rec[p: p + 8 * nch]
+        g = p + 8 * nch
+        for m in range(nch):
+            c = int(base[m])
+            for j in range(8):
+                if j:
+                    gap = int(rec[g]); g += 1
+                    if (int(ctrl[m]) >> j) & 1:
+                        gap |= int(rec[g]) << 8; g += 1
+                    c += gap
+                if m * 8 + j < ln:
+                    comps.append(c)
+                    vals.append(np.float32(np.float32(codes[m * 8 + j]) * scale))
+        off.append(len(comps))
+    return np.array(off, np.uint64), np.array(comps, np.uint32), np.array(vals, np.float32)

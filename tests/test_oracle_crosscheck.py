@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from seismic_b200 import Dataset, HostIndex
-from py_reference import PyIndex, PAD
+from py_reference import PyIndex, PAD, decode_dotvbyte
 
 
 def random_index(seed, n_docs=300, dim=60, **build):
@@ -56,3 +56,47 @@ def test_oracle_matches_python_restatement(oracle_mod, seed, build, k, cut, hf, 
         assert ids[i, : counts[i]].tolist() == p_ids, (i, ids[i], p_ids)
         assert np.array_equal(scores[i, : counts[i]], np.array(p_scores, dtype=np.float32)), i
     assert st["blocks_evaluated"] == evaluated
+
+
+def test_dotvbyte_format_and_search_against_python_decoder(oracle_mod):
+    """DotVByte (row a11): an independent decoder of the byte stream recovers every component exactly and every value
+    within half a quantisation step; the oracle's fused decode + search on the packed index equals the Python
+    restatement run on the decoded vectors (ids, score bits)."""
+    index, rng = random_index(7, n_docs=400, dim=3000, n_postings=30, centroid_fraction=0.2)  # gaps >= 256 occur
+    vb = index.convert_to_dotvbyte()
+    off, comps, vals = decode_dotvbyte(vb)
+    o0, c0, v0 = index.forward_csr()
+    assert np.array_equal(off, o0) and np.array_equal(comps, c0)
+    scale = float(vb.view.value_scale)
+    assert np.all(np.abs(vals - v0) <= scale / 2 + 1e-6)
+    assert (np.diff(c0.astype(np.int64))[np.diff(c0.astype(np.int64)) > 0] >= 256).any(), "no 2-byte gap exercised"
+
+    class Decoded(PyIndex):  # the Python search over the decoded vectors, postings of the packed index
+        def __init__(self, host, csr):
+            self.a = host.arrays()
+            self.n_docs, self.dim = host.len, host.dim
+            self.off, self.comps, self.vals = csr
+            self.fo = self.a["fwd_offsets"].astype(np.int64)
+            self.knn = None
+            self._el = csr[0].astype(np.int64)
+
+        def doc_of(self, start):  # posting start = byte offset / 4 of the packed stream
+            return int(np.searchsorted(self.fo, start * 4, side="right")) - 1
+
+        def doc_score(self, q, start, ln):
+            return super().doc_score(q, int(self._el[self.doc_of(start)]), ln)
+
+    py = Decoded(vb, (off, comps, vals))
+    queries = []
+    for _ in range(20):
+        nnz = int(rng.integers(1, 9))
+        c = np.sort(rng.choice(index.dim, size=nnz, replace=False)).astype(np.uint32)
+        queries.append((c, (rng.random(nnz) * 2).astype(np.float32)))
+    qoff = np.cumsum([0] + [len(c) for c, _ in queries]).astype(np.uint64)
+    qc = np.concatenate([c for c, _ in queries])
+    qv = np.concatenate([v for _, v in queries])
+    ids, scores, counts, _ = oracle_mod.batch_search(vb.view, qoff, qc, qv, 5, 3, 0.8, first_sorted=True, n_threads=1)
+    for i, (c, v) in enumerate(queries):
+        p_ids, p_scores, _ = py.search(c, v, 5, 3, 0.8, first_sorted=True)
+        assert counts[i] == len(p_scores) and ids[i, : counts[i]].tolist() == p_ids, i
+        assert np.array_equal(scores[i, : counts[i]], np.array(p_scores, dtype=np.float32)), i
