@@ -23,9 +23,11 @@
 //   k_est     one warp per (query, term): QuantizedSummary::distances (Loop A,
 //             reference src/quantized_summary.rs:64-160), bit-exact accumulation order
 //   k_order   one CTA per query: block order of the first list by estimate, descending
-//             (reference sort_and_search, src/posting_list.rs:162-166)
-//   k_search  persistent, one CTA per SM: block traversal with skip test, forward-index scoring,
-//             bounded top-k (Loop B; reference src/posting_list.rs:115-215, src/utils.rs:12-66)
+//             (reference sort_and_search, src/posting_list.rs:162-166); emits one 16-byte selection entry
+//             per position
+//   k_search  persistent (as many CTAs as fit the SMs, work counter): block traversal with skip test,
+//             forward-index scoring, bounded top-k, Knn::refine (Loop B; reference src/posting_list.rs:115-215,
+//             src/utils.rs:12-66, src/inverted_index.rs:551-593) — search.cuh
 //   k_finish  key -> doc id (id_from_range, reference src/inverted_index.rs:227-233)
 #pragma once
 #include <cuda_fp16.h>

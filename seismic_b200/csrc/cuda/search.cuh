@@ -3,12 +3,12 @@
 // src/inverted_index.rs:180-234).  Persistent kernel; CTAs fetch query ids from an atomic counter.
 //
 // The kernel is a template over the shared-memory representation of the query:
+//   ByteQuery   byte index per vocabulary entry + value array (dim + 1 KB): the default — two dependent loads per
+//               component, the fewest instructions (4 CTAs x 256 threads per SM)
 //   RankQuery   bitmap over the vocabulary + per-word rank + value array (dim/8 + dim/32 + 1 KB = 5.8 KB at
 //               dim 30522): a forward-index component first tests one bit (96 % of the components of a document
-//               are not in the query and stop there); hits fetch their value through popcount ranking.  Small
-//               enough that a dozen CTAs (= independent queries) are resident per SM and hide each other's
-//               dependent-load latencies, and it needs the fewest shared-memory wavefronts per component.
-//   ByteQuery   byte index per vocabulary entry + value array (dim + 1 KB)
+//               are not in the query and stop there); hits fetch their value through popcount ranking.  The only
+//               table that fits a 200 k vocabulary (Rec32 / SeismicIndexLV); 1.2-1.4x the instructions of ByteQuery
 //   HashQuery   4096-slot perfect hash (tag + value, 24 KB), multiplier found by k_terms
 //   DenseQuery  dense f32 vector (dim x 4 B), one 1024-thread CTA per SM; handles ANY query and is the
 //               fallback for queries with more than 255 distinct components.
