@@ -100,3 +100,31 @@ def test_dotvbyte_format_and_search_against_python_decoder(oracle_mod):
         p_ids, p_scores, _ = py.search(c, v, 5, 3, 0.8, first_sorted=True)
         assert counts[i] == len(p_scores) and ids[i, : counts[i]].tolist() == p_ids, i
         assert np.array_equal(scores[i, : counts[i]], np.array(p_scores, dtype=np.float32)), i
+
+
+@pytest.mark.parametrize("seed", range(10, 22))
+def test_oracle_matches_python_restatement_random_configs(oracle_mod, seed):
+    """Random build parameters, k, query_cut, heap_factor (0 .. 1.5), sorted flag, kNN depth and queries with
+    duplicated components (the last duplicate carries the value; the summary merge consumes the first only)."""
+    r0 = np.random.default_rng(seed)
+    build = dict(n_postings=int(r0.integers(5, 120)), centroid_fraction=float(r0.choice([0.05, 0.1, 0.2, 0.5])),
+                 summary_energy=float(r0.choice([0.2, 0.4, 0.7, 1.0])), max_fraction=float(r0.choice([1.0, 1.5, 3.0])),
+                 min_cluster_size=int(r0.integers(1, 4)))
+    index, rng = random_index(seed, n_docs=int(r0.integers(50, 500)), dim=int(r0.integers(20, 200)), **build)
+    n_knn = int(r0.integers(0, 5))
+    if n_knn:
+        g = rng.integers(0, index.len, size=(index.len, 5), dtype=np.uint64)
+        g[rng.random(g.shape) < 0.2] = PAD
+        index.set_knn(g)
+    py = PyIndex(index)
+    k, cut = int(r0.integers(1, 40)), int(r0.integers(1, 8))
+    hf, srt = float(r0.choice([0.0, 0.5, 0.8, 0.9, 1.0, 1.5])), bool(r0.integers(0, 2))
+    for _ in range(12):
+        nnz = int(rng.integers(1, 10))
+        c = np.sort(rng.choice(index.dim, size=nnz, replace=True)).astype(np.uint32)
+        v = (rng.random(nnz) * 2).astype(np.float32)
+        ids, sc, cnt, st = oracle_mod.batch_search(index.view, np.array([0, nnz], np.uint64), c, v, k, cut, hf,
+                                                   n_knn=n_knn, first_sorted=srt, n_threads=1)
+        p_ids, p_sc, ev = py.search(c, v, k, cut, hf, n_knn=n_knn, first_sorted=srt)
+        assert cnt[0] == len(p_ids) and ids[0, : cnt[0]].tolist() == p_ids
+        assert np.array_equal(sc[0, : cnt[0]], np.array(p_sc, np.float32)) and st["blocks_evaluated"] == ev
