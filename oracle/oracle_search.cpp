@@ -238,41 +238,51 @@ float doc_score_t(const SgpuIndexView& v, const float* q, uint64_t start, uint32
     }
     return ((p[0] + p[4]) + (p[2] + p[6])) + ((p[1] + p[5]) + (p[3] + p[7]));
 }
-// DotVByte record (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte): `start` counts 4-byte units of the
-// packed stream, `len` is the number of components.  value = code * scale, then the same accumulation as above.
+// DotVByte record (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte): `start` counts 16-byte units of the
+// packed stream, `len` is the number of components.  The score is the fixed-point dot product scaled ONCE per
+// document — (sum of q[c] * code) * scale — with the same partial-sum order as the other encodings.  So that the
+// CUDA kernel can turn a code into a float with the half-precision conversion unit (the byte is read as an f16
+// subnormal = code * 2^-24, exact), the sum is carried at 2^-24 of its value and the final factor is scale * 2^24;
+// powers of two commute with every rounding involved (no overflow / underflow for |q| in [1e-30, 1e30]).
+constexpr uint32_t VB_UNIT = 16;
 inline uint32_t vb_record_bytes(const SgpuIndexView& v, uint64_t start, uint32_t len) {
-    const uint8_t* rec = (const uint8_t*)v.fwd_values + start * 4;
-    const uint32_t nch = (len + 7) >> 3;
-    const uint8_t* ctrl = rec + ((2 * nch + 3) & ~3u);
-    uint32_t bytes = ((2 * nch + 3) & ~3u) + ((nch + 3) & ~3u) + 8 * nch + 7 * nch;
-    for (uint32_t m = 0; m < nch; ++m) bytes += __builtin_popcount(ctrl[m]);
+    const uint8_t* rec = (const uint8_t*)v.fwd_values + start * VB_UNIT;
+    const uint32_t nch = (len + 7) >> 3, nr = (nch + 7) >> 3;
+    const uint8_t* rounds = rec + 16ull * nch;
+    uint32_t bytes = 16 * nch + 16 * nr;
+    for (uint32_t m = 0; m < nch; ++m) bytes += __builtin_popcount(rounds[16 * (m >> 3) + (m & 7)]);
     return bytes;
 }
 template <int ORDER>
 float doc_score_vbyte(const SgpuIndexView& v, const float* q, uint64_t start, uint32_t len) {
-    const uint8_t* rec = (const uint8_t*)v.fwd_values + start * 4;
-    const uint32_t nch = (len + 7) >> 3;
-    const uint16_t* base = (const uint16_t*)rec;
-    const uint8_t* ctrl = rec + ((2 * nch + 3) & ~3u);
-    const uint8_t* vv = ctrl + ((nch + 3) & ~3u);
-    const uint8_t* gp = vv + 8 * nch;
+    const uint8_t* rec = (const uint8_t*)v.fwd_values + start * VB_UNIT;
+    const uint32_t nch = (len + 7) >> 3, nr = (nch + 7) >> 3;
+    const uint8_t* rounds = rec + 16ull * nch;
+    const uint8_t* exc = rounds + 16ull * nr;
+    const float c24 = 5.9604644775390625e-08f;  // 2^-24
     float p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seq = 0.f;
     for (uint32_t m = 0; m < nch; ++m) {
-        uint32_t c = base[m];
-        for (uint32_t j = 0; j < 8; ++j) {
-            if (j) {
-                uint32_t gap = *gp++;
-                if ((ctrl[m] >> j) & 1) gap |= (uint32_t)(*gp++) << 8;
-                c += gap;
-            }
-            if (m * 8 + j >= len) continue;  // tail padding: gap 0, code 0
-            const float val = (float)vv[m * 8 + j] * v.value_scale;
+        const uint8_t* fx = rec + 16ull * m;
+        const uint32_t ctrl = rounds[16 * (m >> 3) + (m & 7)];
+        if ((m & 7) == 0) {  // the round header's offset must agree with the running position
+            uint32_t eo;
+            std::memcpy(&eo, rounds + 16 * (m >> 3) + 8, 4);
+            exc = rounds + 16ull * nr + eo;
+        }
+        uint32_t c = 0;
+        for (uint32_t f = 0; f < 8; ++f) {
+            uint32_t field = fx[f];
+            if (ctrl & (f == 0 ? 0x80u : (1u << (f - 1)))) field |= (uint32_t)(*exc++) << 8;
+            c = f == 0 ? field : c + field;
+            if (m * 8 + f >= len) continue;  // tail padding: gap 0, code 0
+            const float val = (float)fx[8 + f] * c24;
             if (ORDER == ORDER_SEQ) seq = seq + q[c] * val;
             else p[m & 7] = p[m & 7] + q[c] * val;
         }
     }
-    if (ORDER == ORDER_SEQ) return seq;
-    return ((p[0] + p[4]) + (p[2] + p[6])) + ((p[1] + p[5]) + (p[3] + p[7]));
+    const float s24 = v.value_scale * 16777216.f;
+    if (ORDER == ORDER_SEQ) return seq * s24;
+    return (((p[0] + p[4]) + (p[2] + p[6])) + ((p[1] + p[5]) + (p[3] + p[7]))) * s24;
 }
 template <int ORDER>
 inline float doc_score(const SgpuIndexView& v, const float* q, uint64_t start, uint32_t len) {
@@ -282,7 +292,7 @@ inline float doc_score(const SgpuIndexView& v, const float* q, uint64_t start, u
 }
 // forward-index position (fwd_offsets units: elements, or bytes for DotVByte) of a posting's start field
 inline uint64_t fwd_pos(const SgpuIndexView& v, uint64_t start) {
-    return v.value_kind == SGPU_VAL_DOTVBYTE ? start * 4 : start;
+    return v.value_kind == SGPU_VAL_DOTVBYTE ? start * VB_UNIT : start;
 }
 
 inline uint32_t bits_for(uint64_t n_values) {  // BitField width for values in [0, n_values)
@@ -384,8 +394,8 @@ void search_one(const SgpuIndexView& v, const uint32_t* qc, const float* qv, uin
                 // prefetch_with_range: every cache line of the vector's components and values
                 const uint32_t plen = (uint32_t)(posts[i] & 0xffff);
                 if (vbyte) {
-                    const uint8_t* pr = (const uint8_t*)v.fwd_values + start * 4;
-                    for (uint32_t x = 0; x < plen * 5 / 2 + 64; x += 64) __builtin_prefetch(pr + x);
+                    const uint8_t* pr = (const uint8_t*)v.fwd_values + start * VB_UNIT;
+                    for (uint32_t x = 0; x < plen * 3 + 64; x += 64) __builtin_prefetch(pr + x);
                 } else {
                     const uint8_t* pc = (const uint8_t*)v.fwd_comps + start * cbytes;
                     const uint8_t* pv = (const uint8_t*)v.fwd_values + start * vbytes;
@@ -563,7 +573,7 @@ int oracle_exact_search(const SgpuIndexView* v, const SgpuQueryBatch* qb, uint32
                 for (uint64_t d = 0; d < v->n_docs; ++d) {
                     uint64_t s = v->fwd_offsets[d];
                     uint32_t len = (uint32_t)(v->fwd_offsets[d + 1] - s);
-                    if (v->value_kind == SGPU_VAL_DOTVBYTE) s >>= 2, len = v->fwd_nnz[d];
+                    if (v->value_kind == SGPU_VAL_DOTVBYTE) s /= VB_UNIT, len = v->fwd_nnz[d];
                     if (!len) continue;
                     heap.push(Item{doc_score<ORDER_LANES8>(*v, q.data(), s, len), s, len});
                 }

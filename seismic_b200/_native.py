@@ -18,16 +18,17 @@ REPO = ROOT.parent
 LIB_DIR = ROOT / "_lib"
 LIB_PATH = LIB_DIR / "libseismic_b200.so"
 HOST_SRC = sorted((ROOT / "csrc" / "host").glob("*.cpp"))
-CUDA_SRC = [ROOT / "csrc" / "cuda" / "sgpu_api.cu"]
+CUDA_SRC = sorted((ROOT / "csrc" / "cuda").glob("*.cu"))  # sgpu_api.cu + one translation unit per group of k_search instantiations
 HEADERS = (
     sorted((ROOT / "csrc" / "host").glob("*.hpp"))
     + sorted((ROOT / "csrc" / "cuda").glob("*.cuh"))
     + [REPO / "include" / "seismic_b200.h"]
 )
+OBJ_DIR = LIB_DIR / "obj"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-pthread,-O3,-march=x86-64-v3", "-shared",
+    "-Xcompiler", "-fPIC,-pthread,-O3,-march=x86-64-v3",
 ]
 
 
@@ -39,18 +40,41 @@ def _stale() -> bool:
 
 
 def build_native(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA + host sources into seismic_b200/_lib/libseismic_b200.so for sm_100a."""
+    """Compile the CUDA + host sources into seismic_b200/_lib/libseismic_b200.so for sm_100a.
+    Every source file is its own nvcc -c job (run in parallel), then one link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     LIB_DIR.mkdir(exist_ok=True)
+    OBJ_DIR.mkdir(exist_ok=True)
+    newest_header = max(p.stat().st_mtime for p in HEADERS)
+    extra = os.environ.get("SEISMIC_B200_NVCC_EXTRA", "").split()  # e.g. -DSGPU_...=1 for A/B builds
+    jobs = []
+    for src in CUDA_SRC + HOST_SRC:
+        obj = OBJ_DIR / (src.stem + ".o")
+        if force or extra or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, newest_header):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src.name, res.stdout, res.stderr))
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4) or 1) as ex:
+        list(ex.map(compile_one, jobs))
     tmp = LIB_DIR / (".build_%d.so" % os.getpid())
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp), *map(str, CUDA_SRC), *map(str, HOST_SRC)]
+    objs = [str(OBJ_DIR / (src.stem + ".o")) for src in CUDA_SRC + HOST_SRC]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC,-pthread", "-o", str(tmp), *objs]
     if verbose:
-        print(" ".join(cmd))
+        print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

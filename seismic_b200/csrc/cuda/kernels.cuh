@@ -30,82 +30,17 @@
 //             src/utils.rs:12-66, src/inverted_index.rs:551-593) — search.cuh
 //   k_finish  key -> doc id (id_from_range, reference src/inverted_index.rs:227-233)
 #pragma once
-#include <cuda_fp16.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "types.cuh"
 
 namespace sgpu {
-
-struct ListHdr {
-    uint64_t post_base;  // into postings
-    uint64_t ent_base;   // into ent_blk / ent_code
-    uint64_t sc_base;    // into sc_comp ; run offsets start at sc_base + list id
-    uint64_t blk_base;   // into blk_min / blk_quant ; blk_post_off starts at blk_base + list id
-    uint32_t n_blk;
-    uint32_t n_sc;
-    uint32_t n_post;
-    uint32_t pad;
-};
-
-struct DevIndex {
-    const ListHdr* lists;
-    const uint64_t* postings;
-    const uint32_t* blk_post_off;
-    const float* blk_min;
-    const float* blk_quant;
-    const uint32_t* sc_comp;
-    const uint32_t* sc_run_off;
-    const uint16_t* ent_blk;
-    const uint8_t* ent_code;
-    const uint4* fwd;           // record buffer, 2 x uint4 per chunk
-    const uint32_t* rec_start;  // [n_docs+1]
-    uint64_t n_docs;
-    uint32_t dim;
-    uint32_t comp32;  // 1: u32 components (Rec32 records, 16-byte units), 0: u16 components (Rec16, 32-byte units)
-    uint32_t vbyte;   // 1: DotVByte byte stream (4-byte units), u16 components
-    uint32_t value_kind;  // SGPU_VAL_* of the records
-    float value_scale;
-    const uint64_t* knn_posts;  // [n_docs * knn_dim] neighbours as postings (record start << 16 | padded nnz), ~0 = none
-    uint32_t knn_dim;
-    uint32_t rec_chunk_units;   // units of rec_start per 8-component chunk (plain layouts)
-};
-
-struct Batch {
-    const uint64_t* q_off;
-    const uint32_t* q_comps;
-    const float* q_vals;
-    uint32_t nq;      // queries in this chunk
-    uint32_t q_base;  // first query of the chunk inside the caller's batch
-};
-
-struct Scratch {
-    uint32_t* terms;     // [nq_chunk * cut_eff] list ids, best first
-    uint32_t* nterms;    // [nq]
-    uint32_t* status;    // [nq] 0 ok, 1 invalid
-    float* est;          // [nq_chunk * cut_eff * est_stride]
-    uint4* sel;          // [nq_chunk * est_stride] first list in search order: {estimate bits, first posting, postings, block}
-    uint32_t* counters;  // [0] dense work counter, [1] max nterms, [2] invalid queries, [3] hq work counter,
-                         // [4] number of hq queries, [5] number of dense queries
-    uint32_t* hmult;     // [nq] perfect-hash multiplier of the query (0: dense kernel)
-    uint32_t* cost;      // [nq] scheduling cost proxy (postings of the query's lists)
-    uint32_t* qlist_hq;  // [nq] chunk-relative ids of the queries taken by the hash-query kernel
-    uint32_t* qlist_dense;
-    uint32_t* out_keys;  // [nq_chunk * k]
-    unsigned long long* stats;  // [0..3] docs_scored, blocks_scored, blocks_pushed, fwd_units; [4..9] phase clocks
-    uint32_t est_stride;
-    uint32_t cut_eff;
-};
-
-__device__ __forceinline__ uint32_t total_key(float f) {  // f32::total_cmp as unsigned key
-    uint32_t x = __float_as_uint(f);
-    return (x & 0x80000000u) ? ~x : (x | 0x80000000u);
-}
 
 // ------------------------------------------------------------------------------------------
 // k_prep: one warp per query.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_prep(Batch b, uint32_t dim, uint32_t query_cut, uint32_t* nterms,
-                                              uint32_t* status, uint32_t* counters) {
+__global__ void __launch_bounds__(128) k_prep(Batch b, uint32_t dim, uint32_t query_cut, uint32_t max_nnz_ok,
+                                              uint32_t* nterms, uint32_t* status, uint32_t* prep) {
+    // prep[1] largest nterms, [2] invalid queries, [3] queries longer than any kernel of this index can stage,
+    // [6] largest query nnz
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= b.nq) return;
@@ -118,13 +53,15 @@ __global__ void __launch_bounds__(128) k_prep(Batch b, uint32_t dim, uint32_t qu
         if (i > 0 && b.q_comps[o + i - 1] > c) bad = true;  // is_sorted(): non-decreasing
     }
     bad = __any_sync(0xffffffffu, bad);
+    const bool too_long = n > (uint64_t)max_nnz_ok;
     if (lane == 0) {
-        uint32_t nt = bad ? 0u : (uint32_t)(n < (uint64_t)query_cut ? n : (uint64_t)query_cut);
+        uint32_t nt = (bad || too_long) ? 0u : (uint32_t)(n < (uint64_t)query_cut ? n : (uint64_t)query_cut);
         nterms[q] = nt;
-        status[q] = bad ? 1u : 0u;
-        atomicMax(&counters[1], nt);
-        if (bad) atomicAdd(&counters[2], 1u);
-        atomicMax(&counters[6], (uint32_t)(n < 0xffffffffull ? n : 0xffffffffull));
+        status[q] = bad ? 1u : (too_long ? 2u : 0u);
+        atomicMax(&prep[1], nt);
+        if (bad) atomicAdd(&prep[2], 1u);
+        else if (too_long) atomicAdd(&prep[3], 1u);
+        atomicMax(&prep[6], (uint32_t)(n < 0xffffffffull ? n : 0xffffffffull));
     }
 }
 
@@ -227,16 +164,27 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route(Scratch sc, uint32_t nq
 // ------------------------------------------------------------------------------------------
 // k_est: Loop A.  One warp per (query, term).  est[s] accumulates, for the query components present
 // in the list's summaries IN ASCENDING COMPONENT ORDER, ((code * quant[s]) + min[s]) * qv with four
-// separate roundings (Rust does not contract to FMA).  A summary id occurs at most once per component,
-// so lanes of one component never collide; components are serialised with __syncwarp().
+// separate roundings (Rust does not contract to FMA).
+//
+// The addends do not depend on the accumulation order, only the additions do.  So a batch of up to 64 query
+// components is handled in three lane-parallel steps: (1) every lane binary-searches its component(s) in the
+// list's sorted summary components and fetches the run bounds; (2) the runs of all matched components are
+// laid end to end (warp prefix sum) and the lanes walk that flat entry list — every global load of the batch
+// (entry ids, codes, quants, mins) is independent of every other, so the memory latency is paid once per 32
+// entries instead of once per component — and stage (block id, addend) pairs in shared memory; (3) the staged
+// pairs are added to the accumulators component by component (a summary id occurs at most once per component,
+// so the lanes of one component never collide; components are separated by __syncwarp()).
 // The accumulators live in shared memory when the list has <= EST_SMEM blocks, else directly in the
 // global scratch (same algorithm, L2-coherent accesses).
 // ------------------------------------------------------------------------------------------
 constexpr int EST_WARPS = 4;
-constexpr int EST_SMEM = 1024;  // blocks per warp kept in shared memory (4 x 4 KB); larger lists accumulate in global
+constexpr int EST_SMEM = 1024;   // blocks per warp kept in shared memory (4 x 4 KB); larger lists accumulate in global
+constexpr int EST_STAGE = 512;   // staged (block id, addend) pairs per warp
 
 __global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc) {
     __shared__ float s_est[EST_WARPS][EST_SMEM];
+    __shared__ float s_add[EST_WARPS][EST_STAGE];
+    __shared__ uint16_t s_blk[EST_WARPS][EST_STAGE];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t task = blockIdx.x * EST_WARPS + w;
     const uint32_t q = task / sc.cut_eff, t = task % sc.cut_eff;
@@ -258,44 +206,111 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Sc
     const uint8_t* ec = ix.ent_code + h.ent_base;
     const float* mins = ix.blk_min + h.blk_base;
     const float* quants = ix.blk_quant + h.blk_base;
-    for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t i = base + lane;
-        int32_t found = -1;
-        float qv = 0.f;
-        if (i < n) {
-            const uint32_t c = b.q_comps[o + i];
-            qv = b.q_vals[o + i];
-            const bool dup = i > 0 && b.q_comps[o + i - 1] == c;  // the merge consumes the first duplicate only
-            if (!dup) {
-                uint32_t lo = 0, hi = h.n_sc;
-                while (lo < hi) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(scomp + mid) < c) lo = mid + 1;
-                    else hi = mid;
-                }
-                if (lo < h.n_sc && __ldg(scomp + lo) == c) found = (int32_t)lo;
+    float* st_add = s_add[w];
+    uint16_t* st_blk = s_blk[w];
+    for (uint32_t base = 0; base < n; base += 64) {
+        // ---- (1) lane handles query components base + 2 * lane and base + 2 * lane + 1 (ascending across lanes)
+        uint32_t e0[2] = {0, 0}, len[2] = {0, 0};
+        float qv[2] = {0.f, 0.f};
+        uint32_t lo[2] = {0, 0}, hi[2] = {0, 0}, c[2] = {0, 0};
+        bool want[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t i = base + 2 * lane + u;
+            want[u] = false;
+            if (i < n) {
+                c[u] = b.q_comps[o + i];
+                qv[u] = b.q_vals[o + i];
+                want[u] = !(i > 0 && b.q_comps[o + i - 1] == c[u]);  // the merge consumes the first duplicate only
+                hi[u] = want[u] ? h.n_sc : 0u;
             }
         }
-        uint32_t m = __ballot_sync(0xffffffffu, found >= 0);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t ci = (uint32_t)__shfl_sync(0xffffffffu, found, src);
-            const float wq = __shfl_sync(0xffffffffu, qv, src);
-            const uint32_t e0 = __ldg(run + ci), e1 = __ldg(run + ci + 1);
-            for (uint32_t e = e0 + lane; e < e1; e += 32) {
-                const uint32_t s = __ldg(eb + e);
-                const float code = (float)__ldg(ec + e);
-                const float deq = __fadd_rn(__fmul_rn(code, __ldg(quants + s)), __ldg(mins + s));
-                const float add = __fmul_rn(deq, wq);
-                if (in_smem) {
-                    acc[s] = __fadd_rn(acc[s], add);
-                } else {
-                    float cur = __ldcg(acc + s);
-                    __stcg(acc + s, __fadd_rn(cur, add));
+        while (__any_sync(0xffffffffu, lo[0] < hi[0] || lo[1] < hi[1])) {  // the two searches run interleaved
+            uint32_t mid[2], v[2] = {0, 0};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                mid[u] = (lo[u] + hi[u]) >> 1;
+                if (lo[u] < hi[u]) v[u] = __ldg(scomp + mid[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (lo[u] < hi[u]) {
+                    if (v[u] < c[u]) lo[u] = mid[u] + 1;
+                    else hi[u] = mid[u];
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (want[u] && lo[u] < h.n_sc && __ldg(scomp + lo[u]) == c[u]) {
+                e0[u] = __ldg(run + lo[u]);
+                len[u] = __ldg(run + lo[u] + 1) - e0[u];
+            }
+        // ---- flat entry list of the batch: exclusive prefix sum of the run lengths (slot 2 * lane + u)
+        const uint32_t mine = len[0] + len[1];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft);
+            if (lane >= (uint32_t)sft) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t off0 = incl - mine, off1 = off0 + len[0];  // first flat position of the lane's two runs
+        for (uint32_t w0 = 0; w0 < total; w0 += EST_STAGE) {
+            const uint32_t w1 = min(total, w0 + EST_STAGE);
+            // ---- (2) stage the addends of flat positions [w0, w1)
+            for (uint32_t p0 = w0; p0 < w1; p0 += 32) {
+                const uint32_t p = p0 + lane;
+                const bool act = p < w1;
+                // owner = last lane whose first position is <= p (lanes without entries share their successor's)
+                uint32_t j = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t cand = j + step;
+                    const uint32_t oc = __shfl_sync(0xffffffffu, off0, cand & 31);
+                    if (cand < 32 && oc <= p) j = cand;
+                }
+                const uint32_t j_off0 = __shfl_sync(0xffffffffu, off0, j), j_off1 = __shfl_sync(0xffffffffu, off1, j);
+                const uint32_t j_e0 = __shfl_sync(0xffffffffu, e0[0], j), j_e1 = __shfl_sync(0xffffffffu, e0[1], j);
+                const float j_q0 = __shfl_sync(0xffffffffu, qv[0], j), j_q1 = __shfl_sync(0xffffffffu, qv[1], j);
+                if (act) {
+                    const bool second = p >= j_off1;
+                    const uint32_t e = second ? j_e1 + (p - j_off1) : j_e0 + (p - j_off0);
+                    const float wq = second ? j_q1 : j_q0;
+                    const uint32_t s = __ldg(eb + e);
+                    const float code = (float)__ldg(ec + e);
+                    const float deq = __fadd_rn(__fmul_rn(code, __ldg(quants + s)), __ldg(mins + s));
+                    st_blk[p - w0] = (uint16_t)s;
+                    st_add[p - w0] = __fmul_rn(deq, wq);
                 }
             }
             __syncwarp();
+            // ---- (3) add, one component (= one run) at a time, in ascending component order
+            // slot order is (lane 0, u 0), (lane 0, u 1), (lane 1, u 0), ...: walk the lanes once, u = 0 then u = 1
+            uint32_t m0 = __ballot_sync(0xffffffffu, len[0] > 0 && off0 < w1 && off0 + len[0] > w0);
+            uint32_t m1 = __ballot_sync(0xffffffffu, len[1] > 0 && off1 < w1 && off1 + len[1] > w0);
+            uint32_t mm = m0 | m1;
+            while (mm) {
+                const int src = __ffs(mm) - 1;
+                mm &= mm - 1;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (!(((u ? m1 : m0) >> src) & 1u)) continue;  // warp-uniform
+                    const uint32_t r0 = __shfl_sync(0xffffffffu, u ? off1 : off0, src);
+                    const uint32_t r1 = r0 + __shfl_sync(0xffffffffu, len[u], src);
+                    const uint32_t a0 = max(r0, w0), a1 = min(r1, w1);
+                    for (uint32_t p = a0 + lane; p < a1; p += 32) {
+                        const uint32_t s = st_blk[p - w0];
+                        const float add = st_add[p - w0];
+                        if (in_smem) {
+                            acc[s] = __fadd_rn(acc[s], add);
+                        } else {
+                            const float cur = __ldcg(acc + s);
+                            __stcg(acc + s, __fadd_rn(cur, add));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
         }
     }
     if (in_smem)

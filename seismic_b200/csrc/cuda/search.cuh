@@ -29,7 +29,7 @@
 // (no FMA), then a butterfly reduction (xor 4, 2, 1).  Components that are not in the query contribute
 // q = +0.0, so skipping them (RankQuery) leaves every partial sum bit-identical.
 #pragma once
-#include "kernels.cuh"
+#include "types.cuh"
 
 namespace sgpu {
 
@@ -71,6 +71,7 @@ struct SearchArgs {
     uint32_t buf_docs;         // capacity of the wave buffers (>= wave caps); larger blocks are split
     uint32_t cand_cap;         // capacity of the per-wave candidate-block arrays (<= threads per CTA)
     uint32_t qd_words;         // 32-bit words of the query table (meaning depends on the query type)
+    uint32_t bucket;           // 1: score the documents of a wave longest first (uniform rounds per warp)
     float value_scale;         // DotVByte: value = code * value_scale
     float* out_scores;         // [nq*k] (chunk-relative)
     uint32_t* out_counts;      // [nq]
@@ -268,6 +269,9 @@ struct HashQuery {
         acc = __fadd_rn(acc, __fmul_rn(get(cw & 0xffffu), h_lo(vw)));
         return __fadd_rn(acc, __fmul_rn(get(cw >> 16), h_hi(vw)));
     }
+    __device__ __forceinline__ float mac_f(float acc, uint32_t c, float val) const {
+        return __fadd_rn(acc, __fmul_rn(get(c), val));
+    }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs&, uint32_t tid) {
         vals = reinterpret_cast<float*>(base);
@@ -319,6 +323,14 @@ struct RankQuery {
         acc = mac(acc, cw & 0xffffu, vw, false);
         return mac(acc, cw >> 16, vw, true);
     }
+    __device__ __forceinline__ float mac_f(float acc, uint32_t c, float val) const {
+        const uint32_t w = bm[c >> 5];
+        if ((w >> (c & 31)) & 1u) {
+            const uint32_t r = pre[c >> 5] + __popc(w & ((1u << (c & 31)) - 1u));
+            acc = __fadd_rn(acc, __fmul_rn(vals[r], val));
+        }
+        return acc;
+    }
     template <int T>
     __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t tid) {
         vals = reinterpret_cast<float*>(base);
@@ -349,6 +361,53 @@ struct RankQuery {
     __device__ __forceinline__ void unstage(const Batch& b, uint64_t qo, uint32_t qn, uint32_t tid) {
         for (uint32_t i = tid; i < qn; i += T) bm[b.q_comps[qo + i] >> 5] = 0u;
     }
+};
+
+// The query as it arrives: sorted components (duplicates included) + values, looked up by binary search.  Slow per
+// component (log2(nnz) dependent shared-memory loads) but it takes a query of ANY length on ANY record layout — the
+// path for queries with more than 255 components on the layouts that have no dense-query kernel (u32 components,
+// DotVByte, bf16 / f32 / fixed-point values); e.g. the document-as-query searches of Knn::new
+// (src/inverted_index.rs:448-500).  A duplicated component resolves to its LAST occurrence, like the dense scatter.
+struct SortedQuery {
+    static constexpr bool HAS_DOT8 = false;
+    uint32_t* qc;
+    float* qv;
+    uint32_t n, steps;
+    // qd_words = capacity in components
+    static __device__ __forceinline__ size_t bytes(const SearchArgs& a) { return (size_t)a.qd_words * 8 + 16; }
+    __device__ __forceinline__ float mac_f(float acc, uint32_t c, float val) const {
+        uint32_t lo = 0, len = n;  // upper_bound(qc, c): first position with qc > c
+        for (uint32_t s = 0; s < steps; ++s) {
+            const uint32_t half = len >> 1;
+            const bool right = len > 0 && qc[lo + half] <= c;
+            lo = right ? lo + half + 1 : lo;
+            len = right ? len - half - 1 : half;
+        }
+        if (lo > 0 && qc[lo - 1] == c) acc = __fadd_rn(acc, __fmul_rn(qv[lo - 1], val));
+        return acc;
+    }
+    __device__ __forceinline__ float mac(float acc, uint32_t c, uint32_t vw, bool hi) const {
+        return mac_f(acc, c, hi ? h_hi(vw) : h_lo(vw));
+    }
+    __device__ __forceinline__ float mac2(float acc, uint32_t cw, uint32_t vw) const {
+        acc = mac_f(acc, cw & 0xffffu, h_lo(vw));
+        return mac_f(acc, cw >> 16, h_hi(vw));
+    }
+    template <int T>
+    __device__ __forceinline__ void init(unsigned char* base, const SearchArgs& a, uint32_t) {
+        qc = reinterpret_cast<uint32_t*>(base);
+        qv = reinterpret_cast<float*>(base + (size_t)a.qd_words * 4);
+        n = 0, steps = 0;
+    }
+    template <int T>
+    __device__ __forceinline__ void stage(const Batch& b, const Scratch&, uint32_t, uint64_t qo, uint32_t qn,
+                                          uint32_t tid) {
+        for (uint32_t i = tid; i < qn; i += T) qc[i] = b.q_comps[qo + i], qv[i] = b.q_vals[qo + i];
+        n = qn;
+        steps = 32 - __clz(qn);  // halving a range of n needs floor(log2(n)) + 1 steps to reach length 0
+    }
+    template <int T>
+    __device__ __forceinline__ void unstage(const Batch&, uint64_t, uint32_t, uint32_t) {}
 };
 
 // ---- forward-index record layouts ---------------------------------------------------------------------------
@@ -475,6 +534,50 @@ struct Rec16U8 {  // chunk = [8 x u16 | 8 x u8] = 24 bytes, unit 8 bytes (8-byte
     }
 };
 
+// u32 components x the other plain value encodings ("both u16 and u32"): chunk = [8 x u32 | 8 values].
+// KIND = SGPU_VAL_*: 1 bf16, 2 f32, 3 fixedu8, 4 fixedu16.  Generic per-component q.mac_f path.
+template <int KIND>
+struct Rec32V {
+    static constexpr bool PLAIN_F16 = false;
+    static constexpr int VB = KIND == 2 ? 4 : (KIND == 3 ? 1 : 2);
+    static constexpr int CHUNK_BYTES = 32 + 8 * VB;  // 48, 64 or 40
+    static constexpr int UNIT_BYTES = CHUNK_BYTES % 32 == 0 ? 32 : (CHUNK_BYTES % 16 == 0 ? 16 : 8);
+    static constexpr int WORDS = CHUNK_BYTES / 4;
+    struct Chunk { uint32_t w[WORDS]; };
+    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+        if constexpr (CHUNK_BYTES % 16 == 0) {
+            const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+            for (int i = 0; i < WORDS / 4; ++i) {
+                const uint4 t = ld_stream(p4 + i);
+                k.w[4 * i] = t.x, k.w[4 * i + 1] = t.y, k.w[4 * i + 2] = t.z, k.w[4 * i + 3] = t.w;
+            }
+        } else {
+            const uint2* p2 = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+            for (int i = 0; i < WORDS / 2; ++i) {
+                const uint2 t = __ldg(p2 + i);
+                k.w[2 * i] = t.x, k.w[2 * i + 1] = t.y;
+            }
+        }
+    }
+    static __device__ __forceinline__ float val(const Chunk& k, int e, float scale) {
+        if constexpr (KIND == 2) return __uint_as_float(k.w[8 + e]);
+        else if constexpr (KIND == 3) return __fmul_rn(u_to_f32((k.w[8 + (e >> 2)] >> (8 * (e & 3))) & 0xffu), scale);
+        else {
+            const uint32_t vw = k.w[8 + (e >> 1)];
+            if constexpr (KIND == 1) return __uint_as_float((e & 1) ? (vw & 0xffff0000u) : (vw << 16));
+            else return __fmul_rn(u_to_f32((e & 1) ? (vw >> 16) : (vw & 0xffffu)), scale);
+        }
+    }
+    template <class Q>
+    static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float scale) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = q.mac_f(acc, k.w[e], val(k, e, scale));
+        return acc;
+    }
+};
+
 // Score one document record (nch chunks at `rec`) with an 8-lane group; lane8 handles chunks
 // lane8, lane8+8, ...  The caller reduces the 8 partial sums with group_reduce.
 template <class R, class Q>
@@ -531,126 +634,107 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
 }
 
 // ---- DotVByte records: gap-coded u16 components (1 or 2 bytes per gap) + u8 values --------
-// Format: csrc/host/build.cpp (convert_dotvbyte).  The posting's start field counts 4-byte units of the byte
-// stream.  Each chunk of 8 components is self-contained (absolute base), so lane8 decodes chunks lane8, lane8+8, ...
-// exactly like the plain layouts; the chunk's offset in the gap stream is 7*m + popcount(ctrl[0..m)).
+// Format: csrc/host/build.cpp (convert_dotvbyte).  The posting's start field counts 16-byte units of the byte stream.
+// Per record: 16 bytes per chunk [8 low bytes of (first component, gap 1..7) | 8 codes], then 16 bytes per round of 8
+// chunks [8 control bytes | u32 offset of the round's exception bytes | 0], then the exception area (the high bytes that
+// exist).  lane8 decodes chunk lane8 of every round: one 128-bit load of its chunk, one 128-bit load of the round header
+// (the same address for the 8 lanes of the group), a popcount of the preceding control bytes, an unaligned 8-byte window
+// of the exception area (three aligned 32-bit loads + two funnel shifts), a 256-entry table of byte-permute selectors
+// that spreads the present high bytes to their fields, four byte-permutes that pair low and high bytes into u16 gaps, a
+// packed prefix sum — and the result is exactly a chunk of the plain layout (4 words of two u16 components, 4 words of
+// two f16 values), fed to the same lookup / multiply-add code.  A code byte c is read as the f16 SUBNORMAL c * 2^-24
+// (exact), so the f16 -> f32 conversion of the plain layout doubles as the integer -> float conversion; the factor
+// scale * 2^24 is applied once per document (oracle: doc_score_vbyte).
 struct RecVB {
     static constexpr bool VBYTE = true;
+    static constexpr int UNIT_BYTES = 16;
 };
 template <class R>
 struct is_vbyte { static constexpr bool value = false; };
 template <>
 struct is_vbyte<RecVB> { static constexpr bool value = true; };
 
-// Table entry for a group of four gap fields with 2-byte flags t (bit i: field i has two bytes): field i starts at
-// byte b_i = i + popcount(t & ((1 << i) - 1)) of the group.  x = selectors of fields 0,1 (low half) and 2,3 (high
-// half) for __byte_perm, y / z = masks clearing the second byte of 1-byte fields, w = 8 * popcount(t) = bit offset of
-// the next group beyond its minimum of four bytes.
+// Table entry for control byte t (bit 7: the first component has a high byte, bit f-1: gap f has one).  The present
+// high bytes are consecutive in the exception window, first component first.  x = byte-permute selectors for the high
+// bytes of fields 0..3 (low half) and 4..7 (high half), y / z = masks clearing the absent ones.
 __device__ __forceinline__ uint4 vb_lut_entry(uint32_t t) {
-    uint32_t b[4];
+    uint32_t sel[2] = {0, 0}, msk[2] = {0, 0}, pos = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = i + __popc(t & ((1u << i) - 1u));
-    const uint32_t s01 = b[0] | ((b[0] + 1) << 4) | (b[1] << 8) | ((b[1] + 1) << 12);
-    const uint32_t s23 = b[2] | ((b[2] + 1) << 4) | (b[3] << 8) | (min(b[3] + 1, 7u) << 12);
-    const uint32_t m01 = 0x00ff00ffu | ((t & 1u) ? 0x0000ff00u : 0u) | ((t & 2u) ? 0xff000000u : 0u);
-    const uint32_t m23 = 0x00ff00ffu | ((t & 4u) ? 0x0000ff00u : 0u) | ((t & 8u) ? 0xff000000u : 0u);
-    return make_uint4(s01 | (s23 << 16), m01, m23, 8u * __popc(t));
+    for (uint32_t f = 0; f < 8; ++f) {
+        const bool present = f == 0 ? (t >> 7) & 1u : (t >> (f - 1)) & 1u;
+        if (present) {
+            sel[f >> 2] |= pos << (4 * (f & 3));
+            msk[f >> 2] |= 0xffu << (8 * (f & 3));
+            ++pos;
+        }
+    }
+    return make_uint4(sel[0] | (sel[1] << 16), msk[0], msk[1], pos);
+}
+
+// one chunk of a DotVByte record -> the plain layout's (component words, value words)
+__device__ __forceinline__ void vb_decode(const uint8_t* __restrict__ rec, uint32_t nch, uint32_t m, uint32_t r,
+                                          uint32_t lane8, uint32_t pm0, uint32_t pm1, uint32_t lut_s, uint4& c, uint4& v,
+                                          uint32_t& bytes) {
+    const uint32_t nr = (nch + 7) >> 3;
+    const uint4 fx = ld_stream(reinterpret_cast<const uint4*>(rec) + m);
+    const uint4 rh = ld_stream(reinterpret_cast<const uint4*>(rec) + nch + r);
+    const uint32_t ctrl = __byte_perm(rh.x, rh.y, lane8) & 0xffu;
+    const uint32_t pre = __popc(rh.x & pm0) + __popc(rh.y & pm1);  // exception bytes of the round's earlier chunks
+    const uint8_t* e = rec + 16u * (nch + nr) + rh.z + pre;
+    const uint32_t* ew = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(e) & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(e) & 3u) * 8;
+    const uint32_t w0 = __ldg(ew), w1 = __ldg(ew + 1), w2 = __ldg(ew + 2);
+    const uint32_t X0 = __funnelshift_r(w0, w1, sh), X1 = __funnelshift_r(w1, w2, sh);
+    uint4 lu;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(lu.x), "=r"(lu.y), "=r"(lu.z), "=r"(lu.w) : "r"(lut_s + ctrl * 16));
+    const uint32_t H0 = __byte_perm(X0, X1, lu.x) & lu.y, H1 = __byte_perm(X0, X1, lu.x >> 16) & lu.z;
+    // (low byte, high byte) pairs -> u16 fields, two per word
+    const uint32_t P01 = __byte_perm(fx.x, H0, 0x5140), P23 = __byte_perm(fx.x, H0, 0x7362);
+    const uint32_t P45 = __byte_perm(fx.y, H1, 0x5140), P67 = __byte_perm(fx.y, H1, 0x7362);
+    // packed prefix sum: (a, b) * 0x10001 = (a, a + b); components stay below 2^16, so no carry crosses the halves
+    c.x = P01 * 0x10001u;
+    c.y = (P23 + (c.x >> 16)) * 0x10001u;
+    c.z = (P45 + (c.y >> 16)) * 0x10001u;
+    c.w = (P67 + (c.z >> 16)) * 0x10001u;
+    // codes -> f16 subnormals (code * 2^-24), two per word
+    v.x = __byte_perm(fx.z, 0u, 0x4140);
+    v.y = __byte_perm(fx.z, 0u, 0x4342);
+    v.z = __byte_perm(fx.w, 0u, 0x4140);
+    v.w = __byte_perm(fx.w, 0u, 0x4342);
+    bytes += lu.w;
 }
 
 template <int D, class Q>
 __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream, const uint64_t (&post)[D],
-                                              uint32_t lane8, uint32_t rounds, const Q& q, float scale,
-                                              float (&acc)[D], uint32_t& bytes, uint32_t lut_s) {
+                                              uint32_t lane8, uint32_t rounds, const Q& q, float (&acc)[D],
+                                              uint32_t& bytes, uint32_t lut_s, uint32_t pm0, uint32_t pm1) {
     const uint8_t* rec[D];
     uint32_t nch[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        rec[j] = stream + (post[j] >> 16) * 4;
+        rec[j] = stream + (post[j] >> 16) * RecVB::UNIT_BYTES;
         nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
         acc[j] = 0.f;
-        if (lane8 == 0) bytes += ((2 * nch[j] + 3) & ~3u) + ((nch[j] + 3) & ~3u) + 15 * nch[j];
+        if (lane8 == 0) bytes += 16 * nch[j] + 16 * ((nch[j] + 7) >> 3);
     }
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t m = lane8 + 8 * r;
+        uint4 c[D], v[D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            if (m >= nch[j]) continue;
-            const uint32_t n = nch[j];
-            const uint8_t* ctrl_p = rec[j] + ((2 * n + 3) & ~3u);
-            const uint8_t* vals_p = ctrl_p + ((n + 3) & ~3u);
-            const uint8_t* gaps_p = vals_p + 8 * n;
-            uint32_t c = __ldg(reinterpret_cast<const uint16_t*>(rec[j]) + m);
-            const uint32_t* cw = reinterpret_cast<const uint32_t*>(ctrl_p);
-            uint32_t pc = 0;
-            for (uint32_t w = 0; w < (m >> 2); ++w) pc += __popc(__ldg(cw + w));
-            const uint32_t wlast = __ldg(cw + (m >> 2));
-            pc += __popc(wlast & ((1u << (8 * (m & 3))) - 1u));
-            const uint32_t ctrl = (wlast >> (8 * (m & 3))) & 0xffu;
-            bytes += __popc(ctrl);
-            const uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(vals_p) + 2 * m);
-            const uint32_t v1 = __ldg(reinterpret_cast<const uint32_t*>(vals_p) + 2 * m + 1);
-            // 16-byte window of the gap stream at an arbitrary byte address
-            const uint8_t* g = gaps_p + 7 * m + pc;
-            const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)3);
-            const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(g) & 3u) * 8;
-            const uint32_t w0 = __ldg(gw), w1 = __ldg(gw + 1), w2 = __ldg(gw + 2), w3 = __ldg(gw + 3), w4 = __ldg(gw + 4);
-            // the chunk's gap bytes (7 .. 14 of them) start at byte 0 of the 16-byte window W0..W3
-            const uint32_t W0 = __funnelshift_r(w0, w1, sh), W1 = __funnelshift_r(w1, w2, sh);
-            const uint32_t W2 = __funnelshift_r(w2, w3, sh), W3 = __funnelshift_r(w3, w4, sh);
-            // decode the chunk first (ALU only), then look all eight components up together
-            uint32_t comp[8];
-            float val[8];
-#if SGPU_VB_PRMT
-            // Gaps 1-4 and 5-7 are two groups of (up to) four 1- or 2-byte fields packed in at most 8 bytes each.  A
-            // 16-entry table indexed by the group's 4 control bits gives the byte-permute selectors that spread the
-            // four fields into 16-bit lanes (vb_lut_entry); two PRMT + two AND per group replace seven dependent
-            // 64-bit shift steps.  Group B starts right after group A: 4 + popcount(A's control bits) bytes in.
-            uint4 la, lb;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(la.x), "=r"(la.y), "=r"(la.z), "=r"(la.w) : "r"(lut_s + ((ctrl >> 1) & 0xfu) * 16));
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(lb.x), "=r"(lb.y), "=r"(lb.z), "=r"(lb.w) : "r"(lut_s + (ctrl >> 5) * 16));
-            const uint32_t x01 = __byte_perm(W0, W1, la.x) & la.y, x23 = __byte_perm(W0, W1, la.x >> 16) & la.z;
-            const uint32_t B0 = __funnelshift_rc(W1, W2, la.w), B1 = __funnelshift_rc(W2, W3, la.w);
-            const uint32_t y01 = __byte_perm(B0, B1, lb.x) & lb.y, y23 = __byte_perm(B0, B1, lb.x >> 16) & lb.z;
-            comp[0] = c;
-            comp[1] = comp[0] + (x01 & 0xffffu);
-            comp[2] = comp[1] + (x01 >> 16);
-            comp[3] = comp[2] + (x23 & 0xffffu);
-            comp[4] = comp[3] + (x23 >> 16);
-            comp[5] = comp[4] + (y01 & 0xffffu);
-            comp[6] = comp[5] + (y01 >> 16);
-            comp[7] = comp[6] + (y23 & 0xffffu);
+        for (int j = 0; j < D; ++j) {  // a chunk past the end of a record is (0, +0.0) x 8: adds q * 0 = +-0
+            c[j] = make_uint4(0, 0, 0, 0), v[j] = make_uint4(0, 0, 0, 0);
+            if (m < nch[j]) vb_decode(rec[j], nch[j], m, r, lane8, pm0, pm1, lut_s, c[j], v[j], bytes);
+        }
+        if constexpr (D == 2 && Q::HAS_DOT8) {
+            q.dot2x(acc[0], acc[1], c, v);
+        } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                // 0x4b0000cc (= 2^23 + code as float bits) in one byte permute; minus 2^23 gives (float)code exactly
-                const uint32_t bits = __byte_perm(e < 4 ? v0 : v1, 0x4b000000u, 0x7650u | (uint32_t)(e & 3));
-                val[e] = __fmul_rn(__uint_as_float(bits) - 8388608.f, scale);
-            }
-#else
-            uint64_t lo = ((uint64_t)W1 << 32) | W0, hi = ((uint64_t)W3 << 32) | W2;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (e) {
-                    const bool two = (ctrl >> e) & 1u;
-                    c += (uint32_t)lo & (two ? 0xffffu : 0xffu);
-                    const uint32_t s = two ? 16 : 8;
-                    lo = (lo >> s) | (hi << (64 - s));
-                    hi >>= s;
-                }
-                comp[e] = c;
-                const uint32_t code = ((e < 4 ? v0 : v1) >> (8 * (e & 3))) & 0xffu;
-                // (float)code exactly, without the conversion pipe: 2^23 + code as float bits, minus 2^23
-                val[e] = __fmul_rn(__uint_as_float(0x4b000000u | code) - 8388608.f, scale);
-            }
-#endif
-            if constexpr (Q::HAS_DOT8) {
-                acc[j] = q.dot8f(acc[j], comp, val);
-            } else {
-                float a = acc[j];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a = q.mac_f(a, comp[e], val[e]);
-                acc[j] = a;
+            for (int j = 0; j < D; ++j) {
+                acc[j] = q.mac2(acc[j], c[j].x, v[j].x);
+                acc[j] = q.mac2(acc[j], c[j].y, v[j].y);
+                acc[j] = q.mac2(acc[j], c[j].z, v[j].z);
+                acc[j] = q.mac2(acc[j], c[j].w, v[j].w);
             }
         }
     }
@@ -838,12 +922,13 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     uint32_t* heap_k = reinterpret_cast<uint32_t*>(p);    p += ((a.k + 3) & ~3u) * 4;
     uint64_t* docs = reinterpret_cast<uint64_t*>(p);      p += (size_t)a.buf_docs * 8;
     float* scores = reinterpret_cast<float*>(p);          p += (size_t)a.buf_docs * 4;
-    uint32_t* surv = reinterpret_cast<uint32_t*>(p);  // bit d: document d of the wave can still enter the heap
+    uint32_t* surv = reinterpret_cast<uint32_t*>(p);      p += (size_t)((a.buf_docs + 31) / 32) * 4;  // bit d: document d of the wave can still enter the heap
+    uint16_t* perm = reinterpret_cast<uint16_t*>(p);  // scoring order -> wave slot (longest documents first)
 
     __shared__ uint32_t s_q;
-    __shared__ uint4 s_vb_lut[is_vbyte<R>::value ? 16 : 1];  // DotVByte gap decode (vb_lut_entry); visible after the first barrier of the loop
+    __shared__ uint4 s_vb_lut[is_vbyte<R>::value ? 256 : 1];  // DotVByte decode (vb_lut_entry); visible after the first barrier of the loop
     if constexpr (is_vbyte<R>::value)
-        if (threadIdx.x < 16) s_vb_lut[threadIdx.x] = vb_lut_entry(threadIdx.x);
+        for (uint32_t i = threadIdx.x; i < 256; i += T) s_vb_lut[i] = vb_lut_entry(i);
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
     __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0, s_snap_n;
     __shared__ float s_theta;
@@ -857,6 +942,15 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     const uint32_t lane8 = tid & 7, grp = tid >> 3;
     const uint32_t k = a.k;
 
+    // DotVByte: control bytes of the round's chunks BEFORE this lane's (words 0 / 1 of the round header)
+    const uint32_t vb_pm0 = lane8 >= 4 ? 0xffffffffu : (1u << (8 * lane8)) - 1u;
+    const uint32_t vb_pm1 = lane8 <= 4 ? 0u : (1u << (8 * (lane8 - 4))) - 1u;
+    // bytes of a posting's record (DotVByte: without the exception area's exact size, ~4 per chunk)
+    auto rec_bytes = [&](uint64_t pst) -> uint32_t {
+        const uint32_t nch = ((uint32_t)(pst & 0xffffu) + 7) >> 3;
+        if constexpr (is_vbyte<R>::value) return 20 * nch + 16 * ((nch + 7) >> 3);
+        else return nch * R::CHUNK_BYTES;
+    };
     H heap;  // live in warp 0 only
     heap.reset(k, heap_s, heap_k);
     uint32_t st_docs = 0, st_blocks = 0, st_pushed = 0, st_units = 0;  // per-CTA totals fit 32 bits
@@ -864,6 +958,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         for (int i = 0; i < 6; ++i) s_ph[i] = 0;
         s_cnt[0] = s_cnt[1] = 0;
     }
+
     // Phase clock of thread 0.  Deliberately branch-free (one predicated reduction): an `if (tid == 0)` block can
     // leave thread 0 split from its warp across the code that follows, and every shuffle / vote there then takes its
     // divergent slow path (seen with ncu on a variant of this kernel: 4x slower replay).
@@ -896,42 +991,96 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         const float w_theta = s_theta;
         const uint32_t w_wkey = s_wkey;
         for (uint32_t dbase = 0; dbase < n; dbase += D * GROUPS) {  // CTA-uniform trip count
-            if constexpr (!is_vbyte<R>::value && D == 2) {
+            if constexpr (D == 2) {
                 // the next iteration's records -> L2 (lane: document lane8 / 4, 128-byte lines lane8 % 4 and + 4)
-                const uint32_t dn = dbase + D * GROUPS + (lane8 >> 2) * GROUPS + grp;
+                const uint32_t dn = dbase + D * GROUPS + D * grp + (lane8 >> 2);
                 if (dn < n) {
-                    const uint64_t pn = docs[dn];
-                    const uint32_t bytes = (((uint32_t)(pn & 0xffffu) + 7) >> 3) * R::CHUNK_BYTES, ln = (lane8 & 3) * 128;
+                    const uint64_t pn = docs[perm[dn]];
+                    const uint32_t bytes = rec_bytes(pn), ln = (lane8 & 3) * 128;
                     const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pn >> 16) * R::UNIT_BYTES;
                     if (ln < bytes) prefetch_l2(base + ln);
                     if (ln + 512 < bytes) prefetch_l2(base + ln + 512);
                 }
             }
             uint64_t post[D];
+            uint32_t slot[D];
             uint32_t mx = 0;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const uint32_t d = dbase + j * GROUPS + grp;
-                post[j] = d < n ? docs[d] : 0ull;  // nnz 0 -> no loads, score unused
+                const uint32_t d = dbase + D * grp + j;  // a warp takes 4 * D consecutive positions of the order
+                slot[j] = d < n ? perm[d] : 0xffffffffu;
+                post[j] = d < n ? docs[slot[j]] : 0ull;  // nnz 0 -> no loads, score unused
                 mx = max(mx, (uint32_t)(post[j] & 0xffffu));
             }
             const uint32_t rounds = (__reduce_max_sync(0xffffffffu, mx) + 63) >> 6;
             float acc[D];
             if constexpr (is_vbyte<R>::value)
-                score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, a.value_scale,
-                                 acc, st_units, (uint32_t)__cvta_generic_to_shared(s_vb_lut));
+                score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, acc, st_units,
+                                 (uint32_t)__cvta_generic_to_shared(s_vb_lut), vb_pm0, vb_pm1);
             else
                 score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, a.value_scale, acc);
 #pragma unroll
             for (int j = 0; j < D; ++j) {
-                const float s = group_reduce(acc[j]);
-                const uint32_t d = dbase + j * GROUPS + grp;
-                if (lane8 == 0 && d < n && (post[j] & 0xffffu)) {  // nnz 0: an absent kNN neighbour
+                float s = group_reduce(acc[j]);
+                if constexpr (is_vbyte<R>::value) s = __fmul_rn(s, a.value_scale);  // scale * 2^24, once per document
+                const uint32_t d = slot[j];
+                if (lane8 == 0 && d != 0xffffffffu && (post[j] & 0xffffu)) {  // nnz 0: an absent kNN neighbour
                     scores[d] = s;
                     if constexpr (!is_vbyte<R>::value) st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
                     // theta only grows: a document that cannot enter the heap as of the wave start never will
                     if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey)) note_survivor(d, s);
                 }
+            }
+        }
+    };
+    // Fill the wave buffer with n postings (loader(i) = posting of slot i) and fix the scoring order.  A warp scores
+    // 4 * D documents at a time (8 consecutive positions of the order) and every lane walks ceil(nnz / 64) rounds of
+    // the LONGEST of them, so mixing lengths wastes lanes (60 % of the lane slots carry data when documents come in
+    // posting order).  Each warp fills a contiguous segment of the slots and orders it by rounds (>= 4, 3, 2, 1) with
+    // ballots only — no atomics, no barrier: neighbours in the order then have the same number of rounds except at
+    // the few bucket boundaries.  Results do not depend on the order (scores / survivors are stored by wave slot).
+    // The caller provides the barrier that makes docs[] / perm[] visible.
+    auto rounds_bucket = [&](uint64_t pst) -> uint32_t {  // 0: >= 4 rounds ... 3: <= 1 round
+        const uint32_t r = ((uint32_t)(pst & 0xffffu) + 63) >> 6;
+        return 4u - min(max(r, 1u), 4u);
+    };
+    auto fill_wave = [&](uint32_t n, auto loader) {
+        const uint32_t seg = (((n + NW - 1) / NW) + 31) & ~31u;  // slots per warp, a multiple of 32
+        const uint32_t s0 = min(n, warp * seg), s1 = min(n, s0 + seg);
+        uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0;
+        for (uint32_t i0 = s0; i0 < s1; i0 += 32) {  // warp-uniform trip count
+            const uint32_t i = i0 + lane;
+            uint32_t bk = 4;
+            if (i < s1) {
+                const uint64_t pst = loader(i);
+                docs[i] = pst;
+                bk = rounds_bucket(pst);
+                if (!a.bucket) perm[i] = (uint16_t)i;
+            }
+            cnt0 += __popc(__ballot_sync(0xffffffffu, bk == 0));
+            cnt1 += __popc(__ballot_sync(0xffffffffu, bk == 1));
+            cnt2 += __popc(__ballot_sync(0xffffffffu, bk == 2));
+        }
+        if (!a.bucket) return;
+        __syncwarp();
+        uint32_t at[4] = {s0, s0 + cnt0, s0 + cnt0 + cnt1, s0 + cnt0 + cnt1 + cnt2};  // next free position per bucket
+        for (uint32_t i0 = s0; i0 < s1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const uint64_t pst = i < s1 ? docs[i] : 0ull;
+            const uint32_t bk = i < s1 ? rounds_bucket(pst) : 4u;
+#pragma unroll
+            for (uint32_t bb = 0; bb < 4; ++bb) {
+                const uint32_t m = __ballot_sync(0xffffffffu, bk == bb);
+                if (bk == bb) {
+                    const uint32_t pos = at[bb] + __popc(m & ((1u << lane) - 1u));
+                    perm[pos] = (uint16_t)i;
+                    if (pos < T / 4) {  // what the first scoring step of every warp reads: start the DRAM access now
+                        const uint32_t bytes = rec_bytes(pst);
+                        const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pst >> 16) * R::UNIT_BYTES;
+                        for (uint32_t o = 0; o < bytes && o < 1024; o += 128) prefetch_l2(base + o);
+                    }
+                }
+                at[bb] += __popc(m);
             }
         }
     };
@@ -1049,7 +1198,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     // in flight), so the reference evaluates it; score and push it part by part
                     for (uint32_t off = 0; off < big_nd; off += a.buf_docs) {
                         const uint32_t part = min(a.buf_docs, big_nd - off);
-                        for (uint32_t i = tid; i < part; i += T) docs[i] = posts[big_p0 + off + i];
+                        fill_wave(part, [&](uint32_t i) { return posts[big_p0 + off + i]; });
                         for (uint32_t i = tid; i < (part + 31) >> 5; i += T) surv[i] = 0u;
                         __syncthreads();
                         score_wave(part, 0);
@@ -1073,7 +1222,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 // ---------------- phase 2: gather the postings of all candidate blocks into the wave buffer
                 // (flat over document slots; the owning block is found by binary search over cand_end)
                 for (uint32_t i = tid; i < (n_docs + 31) >> 5; i += T) surv[i] = 0u;
-                for (uint32_t i = tid; i < n_docs; i += T) {
+                fill_wave(n_docs, [&](uint32_t i) {
                     uint32_t lo = 0, hi = n_cand - 1;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
@@ -1081,16 +1230,8 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         else hi = mid;
                     }
                     const uint32_t start = lo ? cand_end[lo - 1] : 0u;
-                    const uint64_t pst = posts[cand_p0[lo] + (i - start)];
-                    docs[i] = pst;
-                    if constexpr (!is_vbyte<R>::value) {
-                        if (i < T / 4) {  // what the first scoring step of every warp reads: start the DRAM access now
-                            const uint32_t bytes = (((uint32_t)(pst & 0xffffu) + 7) >> 3) * R::CHUNK_BYTES;
-                            const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pst >> 16) * R::UNIT_BYTES;
-                            for (uint32_t o = 0; o < bytes && o < 1024; o += 128) prefetch_l2(base + o);
-                        }
-                    }
-                }
+                    return posts[cand_p0[lo] + (i - start)];
+                });
                 __syncthreads();
                 lap(2);
                 // ---------------- phase 3: score the wave
@@ -1159,11 +1300,11 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             const uint32_t total = n_snap * a.n_knn;
             for (uint32_t base = 0; base < total; base += a.buf_docs) {
                 const uint32_t part = min(a.buf_docs, total - base);
-                for (uint32_t i = tid; i < part; i += T) {
+                fill_wave(part, [&](uint32_t i) {
                     const uint32_t c = base + i;
                     const uint64_t pst = a.ix.knn_posts[(uint64_t)snap[c / a.n_knn] * a.ix.knn_dim + c % a.n_knn];
-                    docs[i] = pst == ~0ull ? 0ull : pst;
-                }
+                    return pst == ~0ull ? 0ull : pst;
+                });
                 for (uint32_t i = tid; i < (part + 31) >> 5; i += T) surv[i] = 0u;
                 __syncthreads();
                 score_wave(part, 0);

@@ -1,0 +1,24 @@
+// Instantiations of k_search live in their own translation units (inst_*.cu, compiled in parallel); the driver
+// (sgpu_api.cu) picks one through these functions.
+#pragma once
+#include "search.cuh"
+
+namespace sgpu {
+
+typedef void (*kern_t)(const SearchArgs);
+enum QueryKind { Q_DENSE = 0, Q_BYTE = 1, Q_HASH = 2, Q_RANK = 3, Q_SORTED = 4 };
+
+// u16 components, f16 values (the benchmark layout): every query representation
+kern_t pick_rec16(QueryKind q, bool small_k);
+// u32 components, f16 values (SeismicIndexLV): Q_RANK, Q_SORTED
+kern_t pick_rec32(QueryKind q, bool small_k);
+// DotVByte: Q_BYTE, Q_SORTED
+kern_t pick_vb(QueryKind q, bool small_k);
+// u16 components, value_kind in {BF16, F32, FIXEDU8, FIXEDU16}: Q_BYTE, Q_SORTED
+kern_t pick_rec16v(uint32_t value_kind, QueryKind q, bool small_k);
+// u32 components, value_kind in {BF16, F32, FIXEDU8, FIXEDU16}: Q_RANK, Q_SORTED
+kern_t pick_rec32v(uint32_t value_kind, QueryKind q, bool small_k);
+
+#define SGPU_K(T, OCC, Q, R) (small_k ? (kern_t)k_search<T, OCC, 2, Q, RegHeap, R> : (kern_t)k_search<T, OCC, 2, Q, SmemHeap, R>)
+
+}  // namespace sgpu

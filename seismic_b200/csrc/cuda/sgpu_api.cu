@@ -11,7 +11,7 @@
 #include "../../../include/seismic_b200.h"
 #include "exact.cuh"
 #include "kernels.cuh"
-#include "search.cuh"
+#include "search_kernels.cuh"
 
 namespace shost {
 void set_error(const std::string& msg);
@@ -90,16 +90,15 @@ struct SgpuIndex {
     uint32_t hq_wave_docs = 768, hq_first_wave_docs = 128;  // compact-query kernel
     int hq_enabled = 1, hq_ctas_per_sm = 0;
     int hq_mode = 1;  // compact query: 1 byte index, 2 perfect hash, 3 bitmap + rank
-    int hq_threads = 256;
     int hq_cand_cap = 256;    // candidate blocks per wave of the compact kernel
     int hq_carveout_pct = 0;  // shared-memory carveout of the compact kernel in % of the SM maximum (0: smallest that fits)
-    int hq_occ = 4;   // CTAs per SM the 256-thread compact kernel is compiled for (4: 64 registers, 3: 80 registers)
+    int bucket = 1;   // score the documents of a wave longest first (uniform rounds per warp)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
     // per-batch scratch (grow-only)
     DevBuf d_qoff, d_qcomps, d_qvals, d_nterms, d_status, d_counters, d_terms, d_est, d_order, d_keys, d_stats;
-    DevBuf d_out_ids, d_out_scores, d_out_counts, d_hmult, d_qlist;
-    PinnedBuf h_in, h_out;
+    DevBuf d_out_ids, d_out_scores, d_out_counts, d_hmult, d_qlist, d_prep;
+    PinnedBuf h_in, h_out, h_ctl;
     ~SgpuIndex() {
         cudaSetDevice(device);
         for (auto& e : ev)
@@ -153,16 +152,16 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     }
     const bool vbyte = v->value_kind == SGPU_VAL_DOTVBYTE;
     if ((v->comp_bits != 16 && v->comp_bits != 32) || v->value_kind > SGPU_VAL_DOTVBYTE ||
-        (v->comp_bits == 32 && v->value_kind != SGPU_VAL_F16) || (vbyte && !v->fwd_nnz)) {
-        shost::set_error("sgpu_index_create: supported forward indexes are u16 components with f16 / bf16 / f32 / "
-                         "fixedu8 / fixedu16 / DotVByte values and u32 components with f16 values");
+        (v->comp_bits == 32 && vbyte) || (vbyte && !v->fwd_nnz)) {
+        shost::set_error("sgpu_index_create: supported forward indexes are u16 / u32 components with f16 / bf16 / f32 / "
+                         "fixedu8 / fixedu16 values and u16 components with DotVByte values");
         return SGPU_EUNSUPPORTED;
     }
     // record geometry of the plain layouts: chunk = 8 components + 8 values; unit of rec_start / posting starts
     const uint32_t kind = v->value_kind;
     const uint32_t val_bytes = kind == SGPU_VAL_F32 ? 4 : (kind == SGPU_VAL_FIXEDU8 ? 1 : 2);
     const uint32_t chunk_bytes = 8 * ((v->comp_bits == 32 ? 4 : 2) + val_bytes);
-    const uint32_t unit_bytes = chunk_bytes == 32 ? 32 : (chunk_bytes == 48 ? 16 : 8);
+    const uint32_t unit_bytes = chunk_bytes % 32 == 0 ? 32 : (chunk_bytes % 16 == 0 ? 16 : 8);
     const uint32_t chunk_units = chunk_bytes / unit_bytes;
     const bool fast_pack = kind == SGPU_VAL_F16;  // dedicated pack kernels for the two benchmark layouts
     const bool comp32 = v->comp_bits == 32;
@@ -199,13 +198,19 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
 
     // ---- record layout
     std::vector<uint32_t> rec_start(N + 1);
-    if (vbyte) {  // the packed byte stream is the record buffer; rec_start in 4-byte units
+    if (vbyte) {  // the packed byte stream is the record buffer; rec_start in 16-byte units
         const uint64_t bytes = v->fwd_offsets[N];
-        if ((bytes >> 2) >= (1ull << 32)) {
+        if ((bytes >> 4) >= (1ull << 32)) {
             shost::set_error("forward index larger than 2^32 record units");
             return SGPU_EUNSUPPORTED;
         }
-        for (uint64_t d = 0; d <= N; ++d) rec_start[d] = (uint32_t)(v->fwd_offsets[d] >> 2);
+        for (uint64_t d = 0; d <= N; ++d) {
+            if (v->fwd_offsets[d] & 15) {
+                shost::set_error("DotVByte records must be 16-byte aligned");
+                return SGPU_EINVAL;
+            }
+            rec_start[d] = (uint32_t)(v->fwd_offsets[d] >> 4);
+        }
         CK(ix->fwd.ensure(bytes + 64));
         CK(cudaMemsetAsync((char*)ix->fwd.p + bytes, 0, 64, st));
         if (bytes) CK(cudaMemcpyAsync(ix->fwd.p, v->fwd_values, bytes, cudaMemcpyHostToDevice, st));
@@ -338,9 +343,76 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     return SGPU_OK;
 }
 
+// ---- batched search: everything is enqueued on the index's stream without a host round trip ------------------
+// enqueue_search() launches the whole pipeline (k_prep .. k_finish); finish_search() synchronises once, reads the
+// validation counters / statistics that the kernels left in device memory, and reports errors.  The only cases that
+// need the host in the middle are (a) query_cut > FAST_CUT, where the scratch is sized by the largest number of terms
+// any query really has, (b) batches whose scratch exceeds the budget (processed chunk by chunk) and (c) queries too
+// long for the compact query table on layouts without the dense-query kernel (a second pass of the sorted-query
+// kernel over just those queries).
+constexpr uint32_t FAST_CUT = 16;
+
+struct Pending {
+    bool active = false;
+    bool events_pending = false;  // single chunk: ev[2..6] are read in finish_search
+    bool long_pass_pending = false;
+    uint32_t launches = 0, ctas_per_sm = 0, nq = 0, k = 0, vkind = 0;
+    float ms_terms = 0.f, ms_sum = 0.f, ms_search = 0.f, ms_fin = 0.f;
+    // what the deferred long-query pass needs
+    void (*k_long)(const SearchArgs) = nullptr;
+    SearchArgs a_long{};
+    int long_ctas = 0, long_threads = 0;
+    size_t long_smem = 0;
+    uint64_t* d_ids = nullptr;
+};
+
+struct HostCtl {  // pinned
+    uint32_t prep[8];
+    uint32_t counters[8];
+    unsigned long long stats[12];
+};
+
+int collect_chunk_times(SgpuIndex* ix, Pending& pd) {
+    float ms;
+    CK(cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3])); pd.ms_terms += ms;
+    CK(cudaEventElapsedTime(&ms, ix->ev[3], ix->ev[4])); pd.ms_sum += ms;
+    CK(cudaEventElapsedTime(&ms, ix->ev[4], ix->ev[5])); pd.ms_search += ms;
+    CK(cudaEventElapsedTime(&ms, ix->ev[5], ix->ev[6])); pd.ms_fin += ms;
+    return SGPU_OK;
+}
+
+// second pass over the queries the compact query table cannot hold (layouts without the dense-query kernel)
+int run_long_pass(SgpuIndex* ix, Pending& pd, uint32_t max_nnz, uint32_t n_chunk, uint64_t* d_ids_chunk) {
+    cudaStream_t st = ix->stream;
+    SearchArgs al = pd.a_long;
+    al.qd_words = max_nnz;  // SortedQuery: capacity in components
+    const size_t smem = pd.long_smem + (size_t)al.qd_words * 8 + 16;  // SortedQuery::bytes
+    if (smem + 1024 > ix->smem_optin) {
+        shost::set_error("a query has more components (" + std::to_string(max_nnz) +
+                         ") than the sorted-query kernel can stage in shared memory");
+        return SGPU_EUNSUPPORTED;
+    }
+    CK(cudaFuncSetAttribute(pd.k_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pd.k_long, pd.long_threads, smem));
+    if (occ < 1) {
+        shost::set_error("sorted-query kernel does not fit");
+        return SGPU_EUNSUPPORTED;
+    }
+    pd.k_long<<<occ * ix->n_sm, pd.long_threads, smem, st>>>(al);
+    CK(cudaGetLastError());
+    const uint64_t tot = (uint64_t)n_chunk * pd.k;
+    k_finish<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ix->ix.rec_start, ix->ix.n_docs, al.sc.out_keys, al.out_counts,
+                                                            pd.k, n_chunk, d_ids_chunk);
+    CK(cudaGetLastError());
+    pd.launches += 2;
+    return SGPU_OK;
+}
+
 // Device-resident batch search. All pointers are device pointers on ix->device.
-int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchParams* p, uint64_t* d_ids,
-                       float* d_scores, uint32_t* d_counts, SgpuSearchStats* stats) {
+int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchParams* p, uint64_t* d_ids,
+                   float* d_scores, uint32_t* d_counts, Pending& pd) {
+    pd = Pending{};
     if (!ix || !dq || !p || !d_ids || !d_scores || !d_counts) {
         shost::set_error("sgpu_batch_search: null argument");
         return SGPU_EINVAL;
@@ -360,49 +432,26 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     CK(cudaSetDevice(ix->device));
     cudaStream_t st = ix->stream;
     const uint32_t nq = (uint32_t)dq->n_queries;
-    if (stats) std::memset(stats, 0, sizeof(*stats));
     if (nq == 0) return SGPU_OK;
     const uint32_t k = p->k;
-    uint32_t launches = 0;
+    pd.nq = nq;
+    pd.k = k;
+    pd.vkind = ix->ix.value_kind;
+    pd.d_ids = d_ids;
 
     CK(ix->d_nterms.ensure((size_t)nq * 4));
     CK(ix->d_status.ensure((size_t)nq * 4));
+    CK(ix->d_prep.ensure(32));
     CK(ix->d_counters.ensure(32));
     CK(ix->d_stats.ensure(12 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ix->d_counters.p, 0, 32, st));
+    CK(ix->h_ctl.ensure(sizeof(HostCtl)));
+    HostCtl* hc = ix->h_ctl.as<HostCtl>();
+    CK(cudaMemsetAsync(ix->d_prep.p, 0, 32, st));
     CK(cudaMemsetAsync(ix->d_stats.p, 0, 12 * sizeof(unsigned long long), st));
 
-    CK(cudaEventRecord(ix->ev[0], st));
-    Batch all{dq->offsets, dq->comps, dq->values, nq, 0};
-    k_prep<<<(nq + 3) / 4, 128, 0, st>>>(all, ix->ix.dim, p->query_cut, ix->d_nterms.as<uint32_t>(),
-                                         ix->d_status.as<uint32_t>(), ix->d_counters.as<uint32_t>());
-    CK(cudaGetLastError());
-    ++launches;
-    uint32_t h_all[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CK(cudaMemcpyAsync(h_all, ix->d_counters.p, 32, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const uint32_t h_counters[4] = {h_all[0], h_all[1], h_all[2], h_all[6]};  // [3] = largest query nnz
-    if (h_counters[2] != 0) {
-        shost::set_error("Query components must be sorted in ascending order and be < dim (" +
-                         std::to_string(h_counters[2]) + " invalid queries)");
-        return SGPU_EINVAL;
-    }
-    CK(cudaEventRecord(ix->ev[1], st));
-    const uint32_t cut_eff = std::max(1u, h_counters[1]);
-    const uint32_t est_stride = std::max(32u, (ix->max_blocks + 31u) & ~31u);
-    // chunk the batch so that the estimate scratch stays within budget
-    const uint64_t per_query = (uint64_t)cut_eff * est_stride * 4 + (uint64_t)est_stride * 16 + (uint64_t)cut_eff * 4 +
-                               (uint64_t)k * 4 + 12;
-    uint32_t chunk = (uint32_t)std::min<uint64_t>(nq, std::max<uint64_t>(1, ix->scratch_bytes / per_query));
-    CK(ix->d_terms.ensure((size_t)chunk * cut_eff * 4));
-    CK(ix->d_est.ensure((size_t)chunk * cut_eff * est_stride * 4));
-    CK(ix->d_order.ensure((size_t)chunk * est_stride * 16));
-    CK(ix->d_keys.ensure((size_t)chunk * k * 4));
-    CK(ix->d_hmult.ensure((size_t)chunk * 8));
-    CK(ix->d_qlist.ensure((size_t)chunk * 8));
-
-    // ---- launch plans: the dense-query kernel (1 CTA / SM, any query) and the compact-query kernel
-    // (many CTAs / SM; bitmap+rank, byte-indexed or perfect-hash query)
+    // ---- launch plans: the compact-query kernel (many CTAs / SM; byte-indexed, perfect-hash or bitmap+rank query
+    // table, <= 255 distinct components) and the kernel for longer queries (dense f32 query for the u16/f16 layout,
+    // sorted-query binary search elsewhere)
     const size_t heap_bytes = 2 * (size_t)((k + 3) & ~3u) * 4;
     const bool small_k = k <= 32;
     SearchArgs ad{};
@@ -418,20 +467,20 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ad.cand_cap = DENSE_THREADS;
     ad.qd_words = (ix->ix.dim + 31u) & ~31u;
     ad.counter_idx = 0;
+    ad.bucket = ix->bucket ? 1u : 0u;
     const int ctas = std::max(1, ix->ctas);
-    auto wave_bytes = [&](const SearchArgs& x, int) {
-        return 4 * (size_t)x.cand_cap * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 + 16;
+    auto wave_bytes = [&](const SearchArgs& x) {
+        return 4 * (size_t)x.cand_cap * 4 + heap_bytes + (size_t)x.buf_docs * 12 + ((x.buf_docs + 31) / 32) * 4 +
+               (size_t)x.buf_docs * 2 + 16;
     };
-    const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad, DENSE_THREADS);
+    const size_t smem_d = (size_t)ad.qd_words * 4 + wave_bytes(ad);
     const bool comp32 = ix->ix.comp32 != 0;
-    const bool vbyte = ix->ix.vbyte != 0;
-    ad.value_scale = ix->ix.value_scale;
+    // DotVByte sums code * 2^-24 and scales once per document (search.cuh, vb_decode)
+    ad.value_scale = ix->ix.vbyte ? ix->ix.value_scale * 16777216.f : ix->ix.value_scale;
     const uint32_t vkind = ix->ix.value_kind;
-    const bool plain16 = !comp32 && vkind == SGPU_VAL_F16;  // the layouts that also have the dense-query kernel
+    const bool plain16 = !comp32 && vkind == SGPU_VAL_F16;  // the layout that also has the dense-query kernel
     const bool dense_ok = plain16 && smem_d + 1024 <= ix->smem_optin;
-    typedef void (*kern_t)(const SearchArgs);
-    kern_t kd = small_k ? (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, RegHeap>
-                        : (kern_t)k_search<DENSE_THREADS, 1, 2, DenseQuery, SmemHeap>;
+    kern_t kd = pick_rec16(Q_DENSE, small_k);
     if (dense_ok) CK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
 
     SearchArgs ah = ad;
@@ -440,46 +489,37 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
     ah.buf_docs = std::max(ah.wave_docs, ah.first_wave_docs);
     ah.counter_idx = 3;
     const int mode = comp32 ? 3 : (!plain16 ? 1 : ix->hq_mode);  // 1 byte index, 2 perfect hash, 3 bitmap + rank
-    const bool wide = !plain16 || ix->hq_threads >= 256;  // 256-thread CTAs (4 per SM) instead of 128-thread CTAs
-    const int hq_threads = wide ? 256 : 128;
+    const int hq_threads = 256;
     size_t qbytes = 0;
-    kern_t kh = nullptr;
-#define SGPU_PICK(Q, OCC128, D128)                                                                        \
-    (wide ? (small_k ? (ix->hq_occ == 3 ? (kern_t)k_search<256, 3, 2, Q, RegHeap> : (kern_t)k_search<256, 4, 2, Q, RegHeap>) \
-                     : (kern_t)k_search<256, 4, 2, Q, SmemHeap>)                                          \
-          : (small_k ? (kern_t)k_search<128, OCC128, D128, Q, RegHeap>                                     \
-                     : (kern_t)k_search<128, OCC128, D128, Q, SmemHeap>))
+    kern_t kh = nullptr, kl = nullptr;  // compact-query kernel, sorted-query kernel (layouts without the dense one)
+    const QueryKind qk = mode == 1 ? Q_BYTE : (mode == 2 ? Q_HASH : Q_RANK);
     if (mode == 1) {
         ah.qd_words = ((ix->ix.dim + 15u) / 16u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 4;
-        kh = SGPU_PICK(ByteQuery, 6, 2);
-#define SGPU_REC(R) (small_k ? (kern_t)k_search<256, 4, 2, ByteQuery, RegHeap, R> : (kern_t)k_search<256, 4, 2, ByteQuery, SmemHeap, R>)
-        if (vkind == SGPU_VAL_DOTVBYTE) kh = SGPU_REC(RecVB);
-        else if (vkind == SGPU_VAL_BF16) kh = SGPU_REC(Rec16V2<1>);
-        else if (vkind == SGPU_VAL_FIXEDU16) kh = SGPU_REC(Rec16V2<4>);
-        else if (vkind == SGPU_VAL_F32) kh = SGPU_REC(Rec16F32);
-        else if (vkind == SGPU_VAL_FIXEDU8) kh = SGPU_REC(Rec16U8);
-#undef SGPU_REC
     } else if (mode == 2) {
         qbytes = (size_t)HQ_SLOTS * 6;
-        kh = SGPU_PICK(HashQuery, 6, 2);
     } else {
         ah.qd_words = ((ix->ix.dim + 127u) / 128u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 5;
-        kh = SGPU_PICK(RankQuery, 8, 2);
-        if (comp32)
-            kh = small_k ? (kern_t)k_search<256, 4, 2, RankQuery, RegHeap, Rec32>
-                         : (kern_t)k_search<256, 4, 2, RankQuery, SmemHeap, Rec32>;
     }
-#undef SGPU_PICK
+    if (plain16) kh = pick_rec16(qk, small_k);
+    else if (vkind == SGPU_VAL_DOTVBYTE) kh = pick_vb(qk, small_k), kl = pick_vb(Q_SORTED, small_k);
+    else if (comp32 && vkind == SGPU_VAL_F16) kh = pick_rec32(qk, small_k), kl = pick_rec32(Q_SORTED, small_k);
+    else if (comp32) kh = pick_rec32v(vkind, qk, small_k), kl = pick_rec32v(vkind, Q_SORTED, small_k);
+    else kh = pick_rec16v(vkind, qk, small_k), kl = pick_rec16v(vkind, Q_SORTED, small_k);
+    if (!kh) {
+        shost::set_error("no search kernel for this index layout");
+        return SGPU_EUNSUPPORTED;
+    }
     ah.cand_cap = (uint32_t)std::min(hq_threads, std::max(32, ((ix->hq_cand_cap + 3) / 4) * 4));
-    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah, hq_threads);
+    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah);
     bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
     uint32_t ctas_per_sm = 0;
     if (hq_ok) {
         CK(cudaFuncSetAttribute(kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
         int occ = 0;
+        CK(cudaFuncSetAttribute(kh, cudaFuncAttributePreferredSharedMemoryCarveout, 100));  // not the previous call's
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kh, hq_threads, smem_h));
         if (ix->hq_ctas_per_sm > 0) occ = std::min(occ, ix->hq_ctas_per_sm);
         // Shared memory and L1 share one 256 KB array and the in-flight gathers live in L1: ask for the smallest
@@ -494,6 +534,7 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         hq_ctas = occ * ix->n_sm;
         ctas_per_sm = (uint32_t)occ;
     }
+    pd.ctas_per_sm = ctas_per_sm;
     if (ad.n_knn > 0 && ((hq_ok && k > 4 * ah.cand_cap) || (dense_ok && k > 4 * ad.cand_cap))) {
         shost::set_error("n_knn > 0: k exceeds the snapshot buffer of the search kernel");
         return SGPU_EUNSUPPORTED;
@@ -502,17 +543,48 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         shost::set_error("neither the compact-query nor the dense-query kernel fits this index in shared memory");
         return SGPU_EUNSUPPORTED;
     }
-    // routing (k_terms): queries the compact path cannot take need the dense kernel
+    // the sorted-query kernel shares the wave geometry of the compact kernel; its table is sized per batch
+    const bool sorted_ok = !dense_ok && kl != nullptr;
+    const size_t smem_l_base = wave_bytes(ah) + 32;
+    const uint32_t sorted_cap = sorted_ok && ix->smem_optin > smem_l_base + 2048
+                                    ? (uint32_t)((ix->smem_optin - smem_l_base - 2048) / 8) : 0u;
+    // routing (k_terms): queries the compact table cannot take go to the dense / sorted kernel
     const uint32_t max_nnz_compact = mode == 2 ? (uint32_t)HQ_MAX_NNZ : 255u;
-    if (hq_ok && !dense_ok && mode != 2 && h_counters[3] > 255) {
-        shost::set_error("queries with more than 255 components need the dense-query kernel, which does not fit "
-                         "this vocabulary in shared memory");
-        return SGPU_EUNSUPPORTED;
-    }
-    const uint32_t hq_max_nnz = hq_ok ? (dense_ok ? max_nnz_compact : 0xffffffffu) : 0u;
-    const uint32_t hq_tries = mode == 2 ? (dense_ok ? (uint32_t)HQ_TRIES : 4096u) : 0u;
+    const uint32_t max_nnz_ok = dense_ok ? 0xffffffffu : (sorted_ok ? std::max(sorted_cap, max_nnz_compact) : max_nnz_compact);
+    const uint32_t hq_max_nnz = hq_ok ? max_nnz_compact : 0u;
+    const uint32_t hq_tries = mode == 2 ? (uint32_t)HQ_TRIES : 0u;
 
-    float ms_sum = 0.f, ms_search = 0.f, ms_fin = 0.f, ms_terms = 0.f;
+    CK(cudaEventRecord(ix->ev[0], st));
+    Batch all{dq->offsets, dq->comps, dq->values, nq, 0};
+    k_prep<<<(nq + 3) / 4, 128, 0, st>>>(all, ix->ix.dim, p->query_cut, max_nnz_ok, ix->d_nterms.as<uint32_t>(),
+                                         ix->d_status.as<uint32_t>(), ix->d_prep.as<uint32_t>());
+    CK(cudaGetLastError());
+    ++pd.launches;
+    CK(cudaEventRecord(ix->ev[1], st));
+    uint32_t cut_eff = std::max(1u, p->query_cut);
+    if (p->query_cut > FAST_CUT) {  // size the scratch by what the queries really have
+        CK(cudaMemcpyAsync(hc->prep, ix->d_prep.p, 32, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (hc->prep[2] != 0) {
+            shost::set_error("Query components must be sorted in ascending order and be < dim (" +
+                             std::to_string(hc->prep[2]) + " invalid queries)");
+            return SGPU_EINVAL;
+        }
+        cut_eff = std::max(1u, hc->prep[1]);
+    }
+    const uint32_t est_stride = std::max(32u, (ix->max_blocks + 31u) & ~31u);
+    // chunk the batch so that the estimate scratch stays within budget
+    const uint64_t per_query = (uint64_t)cut_eff * est_stride * 4 + (uint64_t)est_stride * 16 + (uint64_t)cut_eff * 4 +
+                               (uint64_t)k * 4 + 12;
+    const uint32_t chunk = (uint32_t)std::min<uint64_t>(nq, std::max<uint64_t>(1, ix->scratch_bytes / per_query));
+    const bool multi = chunk < nq;
+    CK(ix->d_terms.ensure((size_t)chunk * cut_eff * 4));
+    CK(ix->d_est.ensure((size_t)chunk * cut_eff * est_stride * 4));
+    CK(ix->d_order.ensure((size_t)chunk * est_stride * 16));
+    CK(ix->d_keys.ensure((size_t)chunk * k * 4));
+    CK(ix->d_hmult.ensure((size_t)chunk * 8));
+    CK(ix->d_qlist.ensure((size_t)chunk * 8));
+
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t n = std::min(chunk, nq - q0);
         Batch b{dq->offsets, dq->comps, dq->values, n, q0};
@@ -537,16 +609,16 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
         CK(cudaGetLastError());
         k_route<<<1, ROUTE_THREADS, 0, st>>>(sc, n, cut_eff * ix->max_list_post);
         CK(cudaGetLastError());
-        ++launches;
+        pd.launches += 2;
         CK(cudaEventRecord(ix->ev[3], st));
         const uint64_t tasks = (uint64_t)n * cut_eff;
         k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);
         CK(cudaGetLastError());
-        launches += 2;
+        ++pd.launches;
         if (ad.first_sorted) {
             k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc);
             CK(cudaGetLastError());
-            ++launches;
+            ++pd.launches;
         }
         CK(cudaEventRecord(ix->ev[4], st));
         ad.b = ah.b = b;
@@ -558,14 +630,14 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
             ah.n_list = sc.counters + 4;
             kh<<<hq_ctas, hq_threads, smem_h, st>>>(ah);
             CK(cudaGetLastError());
-            ++launches;
+            ++pd.launches;
         }
         if (dense_ok) {
             ad.qlist = sc.qlist_dense;
             ad.n_list = sc.counters + 5;
             kd<<<ctas, DENSE_THREADS, smem_d, st>>>(ad);
             CK(cudaGetLastError());
-            ++launches;
+            ++pd.launches;
         }
         CK(cudaEventRecord(ix->ev[5], st));
         const uint64_t tot = (uint64_t)n * k;
@@ -573,36 +645,99 @@ int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearch
                                                                 ad.out_counts, k, n, d_ids + (uint64_t)q0 * k);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ix->ev[6], st));
-        ++launches;
+        ++pd.launches;
+        if (sorted_ok) {  // what a long-query pass over this chunk would need
+            pd.k_long = kl;
+            pd.a_long = ah;
+            pd.a_long.qlist = sc.qlist_dense;
+            pd.a_long.n_list = sc.counters + 5;
+            pd.a_long.counter_idx = 0;
+            pd.long_threads = hq_threads;
+            pd.long_smem = smem_l_base;
+        }
+        if (multi) {
+            CK(cudaMemcpyAsync(hc->counters, ix->d_counters.p, 32, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(hc->prep, ix->d_prep.p, 32, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (int rc = collect_chunk_times(ix, pd)) return rc;
+            if (sorted_ok && hc->counters[5] > 0) {
+                if (int rc = run_long_pass(ix, pd, hc->prep[6], n, d_ids + (uint64_t)q0 * k)) return rc;
+                CK(cudaStreamSynchronize(st));
+            }
+        } else {
+            pd.events_pending = true;
+            pd.long_pass_pending = sorted_ok;
+        }
+    }
+    CK(cudaMemcpyAsync(hc->prep, ix->d_prep.p, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc->counters, ix->d_counters.p, 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc->stats, ix->d_stats.p, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    pd.active = true;
+    return SGPU_OK;
+}
+
+// One synchronisation: validation result, statistics, and (rarely) the long-query pass.  *reran is set when results
+// were (re)written after the caller may already have enqueued its device-to-host copies.
+int finish_search(SgpuIndex* ix, Pending& pd, SgpuSearchStats* stats, bool* reran) {
+    if (reran) *reran = false;
+    if (!pd.active) return SGPU_OK;
+    cudaStream_t st = ix->stream;
+    CK(cudaStreamSynchronize(st));
+    HostCtl* hc = ix->h_ctl.as<HostCtl>();
+    if (hc->prep[2] != 0) {
+        shost::set_error("Query components must be sorted in ascending order and be < dim (" +
+                         std::to_string(hc->prep[2]) + " invalid queries)");
+        return SGPU_EINVAL;
+    }
+    if (hc->prep[3] != 0) {
+        shost::set_error(std::to_string(hc->prep[3]) + " queries have more components than the search kernels of this "
+                         "index layout can stage in shared memory");
+        return SGPU_EUNSUPPORTED;
+    }
+    if (pd.events_pending)
+        if (int rc = collect_chunk_times(ix, pd)) return rc;
+    if (pd.long_pass_pending && hc->counters[5] > 0) {
+        CK(cudaEventRecord(ix->ev[4], st));
+        if (int rc = run_long_pass(ix, pd, hc->prep[6], pd.nq, pd.d_ids)) return rc;
+        CK(cudaEventRecord(ix->ev[5], st));
+        CK(cudaMemcpyAsync(hc->stats, ix->d_stats.p, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        float ms;
-        CK(cudaEventElapsedTime(&ms, ix->ev[2], ix->ev[3])); ms_terms += ms;
-        CK(cudaEventElapsedTime(&ms, ix->ev[3], ix->ev[4])); ms_sum += ms;
-        CK(cudaEventElapsedTime(&ms, ix->ev[4], ix->ev[5])); ms_search += ms;
-        CK(cudaEventElapsedTime(&ms, ix->ev[5], ix->ev[6])); ms_fin += ms;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ix->ev[4], ix->ev[5]));
+        pd.ms_search += ms;
+        if (reran) *reran = true;
     }
     if (stats) {
         float ms_prep = 0.f;
         CK(cudaEventElapsedTime(&ms_prep, ix->ev[0], ix->ev[1]));
-        unsigned long long hs[12];
-        CK(cudaMemcpy(hs, ix->d_stats.p, sizeof hs, cudaMemcpyDeviceToHost));
+        const unsigned long long* hs = hc->stats;
         for (int i = 0; i < 6; ++i) stats->phase_cycles[i] = hs[4 + i];
-        stats->ms_prep = ms_prep + ms_terms;
-        stats->ms_summary = ms_sum;
-        stats->ms_search = ms_search;
-        stats->ms_finish = ms_fin;
-        stats->ms_total = stats->ms_prep + ms_sum + ms_search + ms_fin;
-        stats->n_launches = launches;
-        stats->ctas_per_sm = ctas_per_sm;
+        stats->ms_prep = ms_prep + pd.ms_terms;
+        stats->ms_summary = pd.ms_sum;
+        stats->ms_search = pd.ms_search;
+        stats->ms_finish = pd.ms_fin;
+        stats->ms_total = stats->ms_prep + pd.ms_sum + pd.ms_search + pd.ms_fin;
+        stats->n_launches = pd.launches;
+        stats->ctas_per_sm = pd.ctas_per_sm;
         stats->docs_scored = hs[0];
         stats->blocks_scored = hs[1];
         stats->blocks_pushed = hs[2];
         stats->waves = hs[10];
         stats->select_passes = hs[11];
+        const uint32_t vkind = pd.vkind;
         const uint64_t cb = 8ull * ((ix->ix.comp32 ? 4 : 2) + (vkind == SGPU_VAL_F32 ? 4 : (vkind == SGPU_VAL_FIXEDU8 ? 1 : 2)));
         stats->fwd_bytes = hs[3] * (ix->ix.vbyte ? 1ull : cb);
     }
+    pd.active = false;
     return SGPU_OK;
+}
+
+int search_device_impl(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchParams* p, uint64_t* d_ids,
+                       float* d_scores, uint32_t* d_counts, SgpuSearchStats* stats) {
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    Pending pd;
+    if (int rc = enqueue_search(ix, dq, p, d_ids, d_scores, d_counts, pd)) return rc;
+    return finish_search(ix, pd, stats, nullptr);
 }
 
 }  // namespace
@@ -640,6 +775,10 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
         if (value >= 1 && value <= 3) ix->hq_mode = (int)value;
         return SGPU_OK;
     }
+    if (n == "bucket") {
+        ix->bucket = value != 0;
+        return SGPU_OK;
+    }
     if (n == "hq_carveout_pct") {  // 0 = automatic
         ix->hq_carveout_pct = (int)std::min<int64_t>(100, std::max<int64_t>(0, value));
         return SGPU_OK;
@@ -648,9 +787,7 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
         shost::set_error("option values must be positive");
         return SGPU_EINVAL;
     }
-    if (n == "hq_threads") ix->hq_threads = (int)value;
-    else if (n == "hq_occ") ix->hq_occ = (int)value;
-    else if (n == "hq_cand_cap") ix->hq_cand_cap = (int)value;
+    if (n == "hq_cand_cap") ix->hq_cand_cap = (int)value;
     else if (n == "hq_wave_docs") ix->hq_wave_docs = (uint32_t)value;
     else if (n == "hq_first_wave_docs") ix->hq_first_wave_docs = (uint32_t)value;
     else if (n == "hq_ctas_per_sm") ix->hq_ctas_per_sm = (int)value;
@@ -709,15 +846,25 @@ int sgpu_batch_search(SgpuIndex* ix, const SgpuQueryBatch* q, const SgpuSearchPa
     CK(ix->d_out_scores.ensure(o_sc));
     CK(ix->d_out_counts.ensure(o_cnt));
     SgpuQueryBatch dq{nq, ix->d_qoff.as<uint64_t>(), ix->d_qcomps.as<uint32_t>(), ix->d_qvals.as<float>()};
-    int rc = search_device_impl(ix, &dq, p, ix->d_out_ids.as<uint64_t>(), ix->d_out_scores.as<float>(),
-                                ix->d_out_counts.as<uint32_t>(), stats);
-    if (rc != SGPU_OK) return rc;
+    Pending pd;
+    if (int rc = enqueue_search(ix, &dq, p, ix->d_out_ids.as<uint64_t>(), ix->d_out_scores.as<float>(),
+                                ix->d_out_counts.as<uint32_t>(), pd))
+        return rc;
     CK(ix->h_out.ensure(o_ids + o_sc + o_cnt));
     uint8_t* hout = ix->h_out.as<uint8_t>();
-    CK(cudaMemcpyAsync(hout, ix->d_out_ids.p, o_ids, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hout + o_ids, ix->d_out_scores.p, o_sc, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hout + o_ids + o_sc, ix->d_out_counts.p, o_cnt, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    auto copy_out = [&]() -> int {
+        CK(cudaMemcpyAsync(hout, ix->d_out_ids.p, o_ids, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hout + o_ids, ix->d_out_scores.p, o_sc, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hout + o_ids + o_sc, ix->d_out_counts.p, o_cnt, cudaMemcpyDeviceToHost, st));
+        return SGPU_OK;
+    };
+    if (int rc = copy_out()) return rc;
+    bool reran = false;
+    if (int rc = finish_search(ix, pd, stats, &reran)) return rc;  // the one synchronisation of the call
+    if (reran) {
+        if (int rc = copy_out()) return rc;
+        CK(cudaStreamSynchronize(st));
+    }
     std::memcpy(out_ids, hout, o_ids);
     std::memcpy(out_scores, hout + o_ids, o_sc);
     std::memcpy(out_counts, hout + o_ids + o_sc, o_cnt);

@@ -722,20 +722,24 @@ void fill_view(const ShostIndex& idx, SgpuIndexView* v) {
 // DotVByte conversion.  The reference builds a standard u16/f16 index and then converts the
 // forward index to `PackedSparseDataset<DotVByteFixedU8Encoder>` (src/pylib/dotvbyte.rs:195-213), re-packing the
 // postings to the packed storage's ranges (src/inverted_index.rs:237-275).  The byte format of that encoder lives
-// in the absent `vectorium` crate, so this is OUR documented format (not byte-compatible):
+// in the absent `vectorium` crate, so this is OUR documented format (not byte-compatible): a variable-byte code of the
+// component gaps (1 or 2 bytes per gap, stream-vbyte style control bits) + u8 fixed-point values, laid out so that a
+// GPU lane decodes one chunk of 8 components with wide aligned loads and byte permutes.
 //
 //   value    u8 code, value = code * scale, scale = (largest f16 value of the collection) / 255   (FixedU8)
-//   record   4-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)):
-//              base  u16[nch]   absolute first component of each chunk          (padded to 4 bytes)
-//              ctrl  u8[nch]    bit j (1..7): gap j of the chunk takes 2 bytes   (padded to 4 bytes)
-//              vals  u8[8*nch]  codes, tail padded with 0
-//              gaps  per chunk 7 gaps c_j - c_{j-1}, 1 or 2 bytes little endian (variable byte), tail gaps 0
-//   fwd_offsets[i]  byte offset of record i;  fwd_nnz[i] number of components;  postings = (offset/4 << 16) | nnz
-// A chunk is self-contained (absolute base), so the 8 lanes of a GPU group decode 8 chunks in parallel; the offset
-// of chunk m in the gap stream is 7*m + popcount(ctrl[0..m)).
+//   record   16-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)), chunks in rounds of 8 (nr = ceil(nch/8)):
+//     fixed  16 bytes per chunk: lo[8] = LOW bytes of (first component, gap 1, ..., gap 7), then val[8] = the 8 codes
+//            (tail of the last chunk: gap 0, code 0)
+//     round  16 bytes per round: ctrl[8] = control byte of each of the round's chunks, exc_off u32 = offset of the
+//            round's first exception byte inside the record's exception area, u32 0
+//            control byte: bit 7 = the first component has a HIGH byte, bit j-1 = gap j has one (j = 1..7)
+//     exc    the high bytes that exist, chunk after chunk: first component, then gaps 1..7
+//     zero padding to a multiple of 16 bytes
+//   fwd_offsets[i]  byte offset of record i;  fwd_nnz[i] number of components;  postings = (offset/16 << 16) | nnz
+// A chunk is self-contained given its round header (absolute first component; exception offset = exc_off +
+// popcount of the preceding control bytes of the round), so the 8 lanes of a GPU group decode the 8 chunks of a round
+// in parallel.
 namespace shost {
-
-static inline uint32_t vb_header_bytes(uint32_t nch) { return ((2 * nch + 3) & ~3u) + ((nch + 3) & ~3u) + 8 * nch; }
 
 int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     if (in.comp_bits != 16 || in.value_kind != SGPU_VAL_F16) {
@@ -750,24 +754,26 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     float mx = 0.f;
     for (uint64_t i = 0; i < in.nnz; ++i) mx = std::max(mx, f16_bits_to_f32(vals[i]));
     const float scale = mx > 0.f ? mx / 255.f : 1.f;
+    // field f (0..7) of chunk m: the first component (f = 0) or gap f
+    auto field = [&](uint64_t s, uint64_t n, uint32_t m, uint32_t f) -> uint32_t {
+        const uint64_t i = (uint64_t)m * 8 + f;
+        if (i >= n) return 0u;
+        return f == 0 ? (uint32_t)comps[s + i] : (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1];
+    };
     // pass 1: record sizes
     std::vector<uint64_t> boff(N + 1, 0);
     parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t d = b; d < e; ++d) {
             const uint64_t s = off[d], n = off[d + 1] - s;
-            const uint32_t nch = (uint32_t)((n + 7) >> 3);
-            uint64_t bytes = vb_header_bytes(nch);
+            const uint32_t nch = (uint32_t)((n + 7) >> 3), nr = (nch + 7) >> 3;
+            uint64_t bytes = 16ull * nch + 16ull * nr;
             for (uint32_t m = 0; m < nch; ++m)
-                for (uint32_t j = 1; j < 8; ++j) {
-                    const uint64_t i = (uint64_t)m * 8 + j;
-                    const uint32_t gap = i < n ? (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1] : 0u;
-                    bytes += gap < 256 ? 1 : 2;
-                }
-            boff[d + 1] = (bytes + 3) & ~3ull;
+                for (uint32_t f = 0; f < 8; ++f) bytes += field(s, n, m, f) >= 256 ? 1 : 0;
+            boff[d + 1] = (bytes + 15) & ~15ull;
         }
     });
     for (uint64_t d = 0; d < N; ++d) boff[d + 1] += boff[d];
-    if ((boff[N] >> 2) >= (1ull << 48)) { set_error("packed forward index too large"); return SGPU_EUNSUPPORTED; }
+    if ((boff[N] >> 4) >= (1ull << 48)) { set_error("packed forward index too large"); return SGPU_EUNSUPPORTED; }
     auto* idx = new ShostIndex();
     idx->comp_bits = 16;
     idx->value_kind = SGPU_VAL_DOTVBYTE;
@@ -778,37 +784,41 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     idx->config = in.config;
     idx->sec[SEC_FWD_OFFSETS].adopt(boff);
     uint8_t* stream = idx->sec[SEC_FWD_VALUES].alloc<uint8_t>(boff[N] + 32);  // 32 bytes of slack for wide loads
+    std::memset(stream + boff[N], 0, 32);
     uint16_t* nnzs = idx->sec[SEC_FWD_NNZ].alloc<uint16_t>(N);
     parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t d = b; d < e; ++d) {
             const uint64_t s = off[d], n = off[d + 1] - s;
-            const uint32_t nch = (uint32_t)((n + 7) >> 3);
+            const uint32_t nch = (uint32_t)((n + 7) >> 3), nr = (nch + 7) >> 3;
             nnzs[d] = (uint16_t)n;
             uint8_t* rec = stream + boff[d];
-            uint16_t* base = (uint16_t*)rec;
-            uint8_t* ctrl = rec + ((2 * nch + 3) & ~3u);
-            uint8_t* vv = ctrl + ((nch + 3) & ~3u);
-            uint8_t* gp = vv + 8 * nch;
+            std::memset(rec, 0, boff[d + 1] - boff[d]);
+            uint8_t* rounds = rec + 16ull * nch;
+            uint8_t* exc0 = rounds + 16ull * nr;
+            uint8_t* exc = exc0;
             for (uint32_t m = 0; m < nch; ++m) {
-                base[m] = comps[s + (uint64_t)m * 8];
+                if ((m & 7) == 0) {
+                    const uint32_t eo = (uint32_t)(exc - exc0);
+                    std::memcpy(rounds + 16ull * (m >> 3) + 8, &eo, 4);
+                }
+                uint8_t* fx = rec + 16ull * m;
                 uint8_t c = 0;
-                for (uint32_t j = 0; j < 8; ++j) {
-                    const uint64_t i = (uint64_t)m * 8 + j;
-                    float r = i < n ? std::nearbyint(f16_bits_to_f32(vals[s + i]) / scale) : 0.f;
-                    vv[m * 8 + j] = (uint8_t)std::min(255.f, std::max(0.f, r));
-                    if (j == 0) continue;
-                    const uint32_t gap = i < n ? (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1] : 0u;
-                    *gp++ = (uint8_t)(gap & 0xff);
-                    if (gap >= 256) {
-                        *gp++ = (uint8_t)(gap >> 8);
-                        c |= (uint8_t)(1u << j);
+                for (uint32_t f = 0; f < 8; ++f) {
+                    const uint64_t i = (uint64_t)m * 8 + f;
+                    const float r = i < n ? std::nearbyint(f16_bits_to_f32(vals[s + i]) / scale) : 0.f;
+                    fx[8 + f] = (uint8_t)std::min(255.f, std::max(0.f, r));
+                    const uint32_t v = field(s, n, m, f);
+                    fx[f] = (uint8_t)(v & 0xff);
+                    if (v >= 256) {
+                        *exc++ = (uint8_t)(v >> 8);
+                        c |= (uint8_t)(f == 0 ? 0x80u : (1u << (f - 1)));
                     }
                 }
-                ctrl[m] = c;
+                rounds[16ull * (m >> 3) + (m & 7)] = c;
             }
         }
     });
-    // posting lists: same blocks and summaries; postings re-packed to (byte offset / 4, nnz)
+    // posting lists: same blocks and summaries; postings re-packed to (byte offset / 16, nnz)
     for (int sidx : {SEC_LIST_POST_START, SEC_LIST_BLK_START, SEC_BLK_POST_OFF, SEC_BLK_MIN, SEC_BLK_QUANT,
                      SEC_LIST_SC_START, SEC_SC_COMP, SEC_LIST_ENT_START, SEC_SC_RUN_OFF, SEC_ENT_BLK, SEC_ENT_CODE}) {
         idx->sec[sidx].own.assign(in.sec[sidx].ptr, in.sec[sidx].ptr + in.sec[sidx].bytes);
@@ -822,7 +832,7 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
         for (uint64_t i = b; i < e; ++i) {
             const uint64_t start = pin[i] >> 16;
             const uint64_t d = (uint64_t)(std::upper_bound(off, off + N + 1, start) - off) - 1;
-            pout[i] = ((boff[d] >> 2) << 16) | (pin[i] & 0xffff);
+            pout[i] = ((boff[d] >> 4) << 16) | (pin[i] & 0xffff);
         }
     });
     *out = idx;

@@ -144,9 +144,11 @@ class PyIndex:
 
 def decode_dotvbyte(host):
     """Independent decoder of the DotVByte forward index (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte;
-    the reference's own byte format lives in vectorium): per document [u16 first component of every chunk of 8 |
-    pad to 4][control byte per chunk | pad to 4][8 u8 codes per chunk][gap bytes: 7 gaps per chunk, 1 byte, or 2
-    bytes little-endian when the control bit of that position is set].  Returns CSR (offsets, components, values)."""
+    the reference's own byte format lives in vectorium).  Per document, 16-byte aligned: [16 bytes per chunk of 8
+    components: 8 low bytes of (first component, gap 1..7) | 8 u8 codes][16 bytes per round of 8 chunks: 8 control
+    bytes | u32 offset of the round's first exception byte | u32 0][exception area: the high bytes that exist, in
+    order].  Control byte: bit 7 = first component has a high byte, bit j-1 = gap j has one.
+    Returns CSR (offsets, components, values = code * scale, codes)."""
     from seismic_b200 import _native as N
     v = host.view
     n = host.len
@@ -154,27 +156,33 @@ def decode_dotvbyte(host):
     stream = N.np_view(v.fwd_values, int(fo[-1]), np.uint8)
     nnzs = N.np_view(v.fwd_nnz, n, np.uint16)
     scale = np.float32(v.value_scale)
-    off, comps, vals = [0], [], []
+    off, comps, vals, codes = [0], [], [], []
     for d in range(n):
+        assert fo[d] % 16 == 0
         rec = stream[int(fo[d]):int(fo[d + 1])]
         ln = int(nnzs[d])
         nch = (ln + 7) // 8
-        base = rec[: 2 * nch].view(np.uint16)
-        p = (2 * nch + 3) & ~3
-        ctrl = rec[p: p + nch]
-        p += (nch + 3) & ~3
-        codes = rec[p: p + 8 * nch]
-        g = p + 8 * nch
+        nr = (nch + 7) // 8
+        rounds = rec[16 * nch: 16 * (nch + nr)]
+        exc = rec[16 * (nch + nr):]
+        e = 0
         for m in range(nch):
-            c = int(base[m])
-            for j in range(8):
-                if j:
-                    gap = int(rec[g]); g += 1
-                    if (int(ctrl[m]) >> j) & 1:
-                        gap |= int(rec[g]) << 8; g += 1
-                    c += gap
-                if m * 8 + j < ln:
+            fx = rec[16 * m: 16 * m + 16]
+            ctrl = int(rounds[16 * (m // 8) + (m % 8)])
+            if m % 8 == 0:
+                assert int(rounds[16 * (m // 8) + 8: 16 * (m // 8) + 12].view(np.uint32)[0]) == e
+            c = 0
+            for f in range(8):
+                field = int(fx[f])
+                if ctrl & (0x80 if f == 0 else (1 << (f - 1))):
+                    field |= int(exc[e]) << 8
+                    e += 1
+                c = field if f == 0 else c + field
+                if m * 8 + f < ln:
                     comps.append(c)
-                    vals.append(np.float32(np.float32(codes[m * 8 + j]) * scale))
+                    codes.append(int(fx[8 + f]))
+                    vals.append(np.float32(np.float32(fx[8 + f]) * scale))
+                else:
+                    assert field == 0 and fx[8 + f] == 0
         off.append(len(comps))
-    return np.array(off, np.uint64), np.array(comps, np.uint32), np.array(vals, np.float32)
+    return np.array(off, np.uint64), np.array(comps, np.uint32), np.array(vals, np.float32), np.array(codes, np.uint8)

@@ -55,13 +55,14 @@ def test_parity_pruned(oracle_mod, synth_pruned, gpu_pruned, k, cut, hf, srt):
 
 
 @pytest.mark.parametrize("hq", [3, 1, 2, 0])
-@pytest.mark.parametrize("wave,first", [(1, 1), (64, 8), (512, 512), (4096, 4096)])
-def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first, hq):
+@pytest.mark.parametrize("wave,first,bucket", [(1, 1, 1), (64, 8, 0), (64, 8, 1), (512, 512, 1), (4096, 4096, 0), (4096, 4096, 1)])
+def test_wave_sizes_do_not_change_results(oracle_mod, synth_pruned, wave, first, hq, bucket):
     """The speculative wave scheduler is a performance knob only: any wave size replays to the same heap,
     in the hash-query kernel (hq=1) as well as in the dense-query kernel (hq=0)."""
     _, q, index = synth_pruned
     g = GpuIndex(index, 0)
     g.set_option("hq", hq)
+    g.set_option("bucket", bucket)
     g.set_option("wave_docs", wave)
     g.set_option("first_wave_docs", first)
     g.set_option("hq_wave_docs", min(wave, 1024))     # blocks larger than the wave buffer are split
@@ -115,16 +116,59 @@ def test_parity_large_vocabulary(oracle_mod, synth_lv, k, cut, hf, srt):
     assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
 
 
-def test_large_vocabulary_query_limit(synth_lv):
-    """u32 indexes only have the compact (bitmap + rank) query kernel: > 255 components per query is refused."""
+def _long_queries(docs, dim, rng, n=12):
+    """Queries with more than 255 components: whole documents glued together + dense ramps (the document-as-query
+    searches of Knn::new, src/inverted_index.rs:448-500, are of this kind on real corpora)."""
+    comps, vals = [], []
+    for i in range(n):
+        c = np.unique(np.concatenate([docs.vector(j)[0] for j in rng.integers(0, len(docs), size=4 + i)]))
+        if i % 3 == 0:
+            c = np.unique(np.concatenate([c, np.arange(i, dim, max(1, dim // 700), dtype=np.uint32)]))
+        comps.append(c.astype(np.uint32))
+        vals.append((rng.random(len(c), dtype=np.float32) * 2 + 0.01).astype(np.float32))
+    comps.append(np.array([3, 3, 9], np.uint32)); vals.append(np.array([1.0, 2.0, 0.5], np.float32))  # short, with a duplicate
+    off = np.zeros(len(comps) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in comps])
+    assert max(len(c) for c in comps) > 255
+    return off, np.concatenate(comps), np.concatenate(vals)
+
+
+def test_large_vocabulary_long_queries(oracle_mod, synth_lv):
+    """The reference accepts any sorted query (src/inverted_index.rs:172-175).  u32 indexes have no dense-query kernel:
+    queries with more than 255 components take the sorted-query kernel in a second pass."""
     docs, q, index = synth_lv
     g = GpuIndex(index, 0)
-    qc = np.arange(0, 3000, 10, dtype=np.uint32)          # 300 components
-    with pytest.raises(NotImplementedError):
-        g.batch_search(np.array([0, len(qc)], np.uint64), qc, np.ones(len(qc), np.float32), 10, 3, 0.8)
-    qc = qc[:255]
-    ids, scores, counts = g.batch_search(np.array([0, len(qc)], np.uint64), qc, np.ones(len(qc), np.float32), 10, 3, 0.8)
-    assert counts[0] <= 10
+    off, qc, qv = _long_queries(docs, index.dim, np.random.default_rng(11))
+    for k, cut, hf, srt in [(10, 3, 0.8, True), (100, 12, 0.9, False), (10, 1000, 0.7, True)]:
+        ref = oracle_mod.batch_search(index.view, off, qc, qv, k, cut, hf, first_sorted=srt)
+        got = g.batch_search(off, qc, qv, k, cut, hf, first_sorted=srt)
+        assert_same(got, ref, f"LV long queries k={k} cut={cut}")
+    # mixed with ordinary queries in one batch, device entry order preserved
+    off2 = np.concatenate([q.offsets, q.offsets[-1] + off[1:]]).astype(np.uint64)
+    qc2, qv2 = np.concatenate([q.comps, qc]), np.concatenate([q.values, qv])
+    ref = oracle_mod.batch_search(index.view, off2, qc2, qv2, 10, 3, 0.8)
+    got = g.batch_search(off2, qc2, qv2, 10, 3, 0.8)
+    assert_same(got, ref, "LV mixed batch")
+
+
+@pytest.mark.parametrize("value_kind", [N.VAL_BF16, N.VAL_F32, N.VAL_FIXEDU8, N.VAL_FIXEDU16])
+def test_parity_large_vocabulary_value_encodings(oracle_mod, value_kind):
+    """u32 components x bf16 / f32 / fixedu8 / fixedu16 (the other half of the reference's encoding matrix,
+    src/bin/perf_inverted_index.rs:95-139)."""
+    from conftest import build_synth
+    docs, q, index = build_synth(20000, 200, dim=90000, comp_bits=32, n_postings=150, centroid_fraction=0.2,
+                                 value_kind=value_kind)
+    assert index.value_kind == value_kind and index.comp_bits == 32
+    g = GpuIndex(index, 0)
+    for k, cut, hf, srt in [(10, 3, 0.8, True), (50, 6, 0.9, False)]:
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        assert_same(got, ref, f"u32 value_kind={value_kind} k={k}")
+        assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+    off, qc, qv = _long_queries(docs, index.dim, np.random.default_rng(3), n=5)
+    ref = oracle_mod.batch_search(index.view, off, qc, qv, 10, 5, 0.8)
+    got = g.batch_search(off, qc, qv, 10, 5, 0.8)
+    assert_same(got, ref, f"u32 value_kind={value_kind} long queries")
 
 
 @pytest.mark.parametrize("k,cut,hf,srt", [(10, 3, 0.8, True), (10, 3, 0.8, False), (100, 6, 0.9, True)])
@@ -156,7 +200,7 @@ def test_dotvbyte_wide_documents(oracle_mod):
     index = HostIndex.build(Dataset.from_lists(comps, vals, dim=60000), n_postings=50)
     vb = index.convert_to_dotvbyte()
     g = GpuIndex(vb, 0)
-    qc = [np.sort(rng.choice(60000, size=200, replace=False)).astype(np.uint32) for _ in range(40)] + [comps[3][:250], comps[77][:250]]   # compact queries hold <= 255 components
+    qc = [np.sort(rng.choice(60000, size=200, replace=False)).astype(np.uint32) for _ in range(40)] + [comps[3], comps[77], comps[5][:300]]   # > 255 components: sorted-query pass
     qv = [rng.random(len(c), dtype=np.float32) for c in qc]
     off = np.zeros(len(qc) + 1, np.uint64); off[1:] = np.cumsum([len(c) for c in qc])
     ref = oracle_mod.batch_search(vb.view, off, np.concatenate(qc), np.concatenate(qv), 10, 20, 0.0, first_sorted=False)
@@ -168,7 +212,7 @@ def test_dotvbyte_wide_documents(oracle_mod):
 def test_parity_value_encodings(oracle_mod, value_kind):
     """The other forward-index value encodings of the reference (SURVEY §8f #1): bf16, f32, fixedu8, fixedu16."""
     from conftest import build_synth
-    _, q, index = build_synth(20000, 200, dim=3000, n_postings=500, centroid_fraction=0.15, value_kind=value_kind)
+    docs, q, index = build_synth(20000, 200, dim=3000, n_postings=500, centroid_fraction=0.15, value_kind=value_kind)
     assert index.value_kind == value_kind
     g = GpuIndex(index, 0)
     for k, cut, hf, srt in [(10, 3, 0.8, True), (50, 6, 0.9, False)]:
@@ -176,6 +220,10 @@ def test_parity_value_encodings(oracle_mod, value_kind):
         got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
         assert_same(got, ref, f"value_kind={value_kind} k={k}")
         assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+    off, qc, qv = _long_queries(docs, index.dim, np.random.default_rng(4), n=5)
+    ref = oracle_mod.batch_search(index.view, off, qc, qv, 10, 5, 0.8)
+    got = g.batch_search(off, qc, qv, 10, 5, 0.8)
+    assert_same(got, ref, f"value_kind={value_kind} long queries")
 
 
 def test_small_scratch_chunks_the_batch(oracle_mod, synth_small):

@@ -64,29 +64,37 @@ def test_dotvbyte_format_and_search_against_python_decoder(oracle_mod):
     restatement run on the decoded vectors (ids, score bits)."""
     index, rng = random_index(7, n_docs=400, dim=3000, n_postings=30, centroid_fraction=0.2)  # gaps >= 256 occur
     vb = index.convert_to_dotvbyte()
-    off, comps, vals = decode_dotvbyte(vb)
+    off, comps, vals, codes = decode_dotvbyte(vb)
     o0, c0, v0 = index.forward_csr()
+    # SeismicIndexDotVByte.get(id): the host decoder of the library agrees with the independent one
+    for d in (0, 7, index.len - 1):
+        gc, gv = vb.get_doc(d)
+        assert np.array_equal(gc, comps[int(off[d]):int(off[d + 1])]) and np.array_equal(gv, vals[int(off[d]):int(off[d + 1])])
     assert np.array_equal(off, o0) and np.array_equal(comps, c0)
     scale = float(vb.view.value_scale)
     assert np.all(np.abs(vals - v0) <= scale / 2 + 1e-6)
     assert (np.diff(c0.astype(np.int64))[np.diff(c0.astype(np.int64)) > 0] >= 256).any(), "no 2-byte gap exercised"
 
     class Decoded(PyIndex):  # the Python search over the decoded vectors, postings of the packed index
-        def __init__(self, host, csr):
+        def __init__(self, host, csr, codes, scale):
             self.a = host.arrays()
             self.n_docs, self.dim = host.len, host.dim
-            self.off, self.comps, self.vals = csr
+            self.off, self.comps, _ = csr
+            # DotVByte scores are the fixed-point dot product scaled once per document, carried at 2^-24
+            # (oracle_search.cpp, doc_score_vbyte): per-component "value" = code * 2^-24, final factor scale * 2^24
+            self.vals = (codes.astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+            self.s24 = np.float32(np.float32(scale) * np.float32(2.0 ** 24))
             self.fo = self.a["fwd_offsets"].astype(np.int64)
             self.knn = None
             self._el = csr[0].astype(np.int64)
 
-        def doc_of(self, start):  # posting start = byte offset / 4 of the packed stream
-            return int(np.searchsorted(self.fo, start * 4, side="right")) - 1
+        def doc_of(self, start):  # posting start = byte offset / 16 of the packed stream
+            return int(np.searchsorted(self.fo, start * 16, side="right")) - 1
 
         def doc_score(self, q, start, ln):
-            return super().doc_score(q, int(self._el[self.doc_of(start)]), ln)
+            return np.float32(super().doc_score(q, int(self._el[self.doc_of(start)]), ln) * self.s24)
 
-    py = Decoded(vb, (off, comps, vals))
+    py = Decoded(vb, (off, comps, vals), codes, vb.view.value_scale)
     queries = []
     for _ in range(20):
         nnz = int(rng.integers(1, 9))

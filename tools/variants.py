@@ -27,7 +27,7 @@ index = HostIndex.build(docs); del docs
 q = Dataset.synth_queries(cfg, a.queries)
 print("setup s", round(time.time() - t, 1), flush=True)
 gpu = GpuIndex(index, 0)
-defaults = {"hq_carveout_pct": 0, "hq_cand_cap": 256, "hq_occ": 4, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "hq_threads": 256}
+defaults = {"hq_carveout_pct": 0, "hq_cand_cap": 256, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "bucket": 1}
 base = None
 rows = []
 for opt in a.opts:
@@ -49,7 +49,7 @@ for opt in a.opts:
         same = bool(np.array_equal(ids, base[0]) and np.array_equal(sc.view(np.uint32), base[1].view(np.uint32))
                     and np.array_equal(cnt, base[2]))
         tot = float(sum(best["phase_cycles"])) or 1.0
-        row = {"opts": opt, "ms_search": round(best["ms_search"], 3), "ms_total": round(best["ms_total"], 3),
+        row = {"opts": opt, "ms_search": round(best["ms_search"], 3), "ms_total": round(best["ms_total"], 3), "ms_summary": round(best["ms_summary"], 3), "ms_prep": round(best["ms_prep"], 3),
                "same_results": same, "docs_scored": best["docs_scored"], "ctas_per_sm": best.get("ctas_per_sm"), "waves": best.get("waves"), "passes": best.get("select_passes"),
                "phase_share": [round(c / tot, 3) for c in best["phase_cycles"]]}
     except Exception as e:  # e.g. a configuration that does not fit shared memory
