@@ -177,17 +177,56 @@ class _IndexBase:
             out[lo:hi] = rows
         self._attach_knn(out)
 
+    _KNN_SIDECAR = ".knn"  # <index file>.knn: the graph of an index saved with one (InvertedIndexBase.knn: Option<Knn>)
+
+    def _write_knn_file(self, file_path: str) -> None:
+        knn = self._host.knn
+        tmp = "%s.tmp%d" % (file_path, os.getpid())
+        with open(tmp, "wb") as f:
+            f.write(self._KNN_MAGIC)
+            f.write(np.array(knn.shape, dtype=np.uint64).tobytes())
+            f.write(np.ascontiguousarray(knn).tobytes())
+        os.replace(tmp, file_path)
+
+    @classmethod
+    def _read_knn_file(cls, file_path: str) -> np.ndarray:
+        with open(file_path, "rb") as f:
+            if f.read(8) != cls._KNN_MAGIC:
+                raise OSError("%s is not a kNN file of this library" % file_path)
+            n_vecs, dim = (int(x) for x in np.frombuffer(f.read(16), dtype=np.uint64))
+            raw = f.read(n_vecs * dim * 8)
+            if len(raw) != n_vecs * dim * 8:
+                raise OSError("%s is truncated" % file_path)
+            return np.frombuffer(raw, dtype=np.uint64).reshape(n_vecs, dim)
+
+    def _save_host(self, index_file: str) -> None:
+        """The index container + (like the reference, which serialises `knn: Option<Knn>` inside the index,
+        src/inverted_index.rs:38-52) the attached kNN graph, as <index_file>.knn."""
+        self._host.save(index_file)
+        side = index_file + self._KNN_SIDECAR
+        if self._host.knn is not None:
+            self._write_knn_file(side)
+        elif os.path.exists(side):
+            os.remove(side)  # an index saved without a graph must not pick up a stale one
+
+    @classmethod
+    def _load_host(cls, index_file: str) -> HostIndex:
+        host = HostIndex.load(index_file)
+        side = index_file + cls._KNN_SIDECAR
+        if os.path.exists(side):
+            nb = cls._read_knn_file(side)
+            if nb.shape[0] != host.len:
+                raise OSError("%s does not belong to %s" % (side, index_file))
+            host.set_knn(np.ascontiguousarray(nb))
+        return host
+
     def save_knn(self, path: str) -> None:
         """Writes <path>.knn.seismic (Knn::serialize, src/inverted_index.rs:542-548).  Own flat format (the reference's
         byte encoding lives in vectorium): magic, n_vecs u64, dim u64, then n_vecs * dim u64 ids."""
-        knn = self._host.knn
-        if knn is None:
+        if self._host.knn is None:
             raise ValueError("No KNN graph is attached to the index.")  # PyValueError, src/pylib/mod.rs:260-264
         try:
-            with open(path + ".knn.seismic", "wb") as f:
-                f.write(self._KNN_MAGIC)
-                f.write(np.array(knn.shape, dtype=np.uint64).tobytes())
-                f.write(np.ascontiguousarray(knn).tobytes())
+            self._write_knn_file(path + ".knn.seismic")
         except OSError:
             raise
         except Exception as e:
@@ -195,11 +234,8 @@ class _IndexBase:
 
     def load_knn(self, knn_path: str, nknn: Optional[int] = None) -> None:
         """Knn::new_from_serialized (src/inverted_index.rs:502-540): optionally keep only the first nknn neighbours."""
-        with open(knn_path, "rb") as f:
-            if f.read(8) != self._KNN_MAGIC:
-                raise OSError("%s is not a kNN file of this library" % knn_path)
-            n_vecs, dim = (int(x) for x in np.frombuffer(f.read(16), dtype=np.uint64))
-            nb = np.frombuffer(f.read(n_vecs * dim * 8), dtype=np.uint64).reshape(n_vecs, dim)
+        nb = self._read_knn_file(knn_path)
+        n_vecs, dim = nb.shape
         if n_vecs != self._host.len:
             raise ValueError("kNN file holds %d vectors, the index %d" % (n_vecs, self._host.len))
         if nknn is not None:
@@ -363,7 +399,7 @@ class SeismicIndex(_IndexBase):
     # -- persistence: <path>.index.seismic (flat container, see csrc/host/io.cpp) + <path>.index.seismic.meta.json
     def save(self, path: str) -> None:
         try:
-            self._host.save(path + ".index.seismic")
+            self._save_host(path + ".index.seismic")
             with open(path + ".index.seismic" + self._META_SUFFIX, "w", encoding="utf-8") as f:
                 json.dump({"doc_ids": self._doc_ids, "token_to_id": self._token_to_id, "contents": self._contents}, f)
         except OSError:
@@ -374,7 +410,7 @@ class SeismicIndex(_IndexBase):
     @classmethod
     def load(cls, index_path: str):
         try:
-            host = HostIndex.load(index_path)
+            host = cls._load_host(index_path)
             meta = {}
             if os.path.exists(index_path + cls._META_SUFFIX):
                 with open(index_path + cls._META_SUFFIX, "r", encoding="utf-8") as f:
@@ -463,11 +499,11 @@ class SeismicIndexRaw(_IndexBase):
         return cls(HostIndex.build(ds, cfg))._apply_knn_args(nknn, knn_path)
 
     def save(self, path: str) -> None:
-        self._host.save(path + ".index.seismic")
+        self._save_host(path + ".index.seismic")
 
     @classmethod
     def load(cls, index_path: str):
-        return cls(HostIndex.load(index_path))
+        return cls(cls._load_host(index_path))
 
     def search(self, query_components, query_values, k: int, query_cut: int, heap_factor: float, n_knn: int,
                sorted: bool) -> List[Tuple[float, int]]:

@@ -21,14 +21,22 @@ struct ExactArgs {
     const uint32_t* q_comps;
     const float* q_vals;
     uint32_t nq, k, seg_docs, n_seg, qd_words;
+    uint32_t chunk_units;  // rec_start units per 8-component chunk
+    float value_scale;
     uint32_t* part_keys;  // [nq][n_seg][k]
     float* part_scores;
 };
 
+// Q: DenseQuery (f32[dim] in shared memory, vocabularies up to ~50 k) or SortedQuery (any vocabulary / query length,
+// binary search per component); R: any plain record layout.
+template <class Q, class R>
 __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* qd = reinterpret_cast<float*>(smem_raw);
-    unsigned char* p = smem_raw + (size_t)a.qd_words * 4;
+    SearchArgs sa{};
+    sa.qd_words = a.qd_words;
+    Q query;
+    query.template init<EXACT_THREADS>(smem_raw, sa, threadIdx.x);
+    unsigned char* p = smem_raw + ((Q::bytes(sa) + 15) & ~(size_t)15);
     float* heap_s = reinterpret_cast<float*>(p);        p += ((a.k + 3) & ~3u) * 4;
     uint32_t* heap_k = reinterpret_cast<uint32_t*>(p);  p += ((a.k + 3) & ~3u) * 4;
     float* cand_s = reinterpret_cast<float*>(p);        p += EXACT_CAND * 4;
@@ -40,16 +48,11 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
     const uint32_t seg = blockIdx.x / a.nq, qi = blockIdx.x % a.nq;
     const uint64_t qo = a.q_off[qi];
     const uint32_t qn = (uint32_t)(a.q_off[qi + 1] - qo);
-    for (uint32_t i = tid; i < a.qd_words; i += EXACT_THREADS) qd[i] = 0.f;
     if (tid == 0) s_ncand = 0, s_full = 0, s_theta = 0.f, s_wkey = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < qn; i += EXACT_THREADS) {
-        const uint32_t c = a.q_comps[qo + i];
-        if (i + 1 == qn || a.q_comps[qo + i + 1] != c) qd[c] = a.q_vals[qo + i];
-    }
+    const Batch bt{a.q_off, a.q_comps, a.q_vals, a.nq, 0};
+    query.template stage<EXACT_THREADS>(bt, Scratch{}, qi, qo, qn, tid);
     __syncthreads();
-    DenseQuery dq;
-    dq.qd = qd;
     SmemHeap heap;
     heap.reset(a.k, heap_s, heap_k);
     const uint64_t d_lo = (uint64_t)seg * a.seg_docs;
@@ -60,9 +63,10 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
         uint32_t r0 = 0, nch = 0;
         if (d < d_hi) {
             r0 = __ldg(a.rec_start + d);
-            nch = __ldg(a.rec_start + d + 1) - r0;
+            nch = (__ldg(a.rec_start + d + 1) - r0) / a.chunk_units;
         }
-        float s = group_reduce(score_rec<Rec16>(reinterpret_cast<const char*>(a.fwd) + (uint64_t)r0 * 32, nch, lane8, dq, 1.f));
+        float s = group_reduce(score_rec<R>(reinterpret_cast<const char*>(a.fwd) + (uint64_t)r0 * R::UNIT_BYTES, nch, lane8,
+                                            query, a.value_scale));
         if (lane8 == 0 && nch > 0 && (!s_full || better(s, r0, s_theta, s_wkey))) {
             const uint32_t slot = atomicAdd(&s_ncand, 1u);
             cand_s[slot] = s;
@@ -70,8 +74,10 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
         }
         __syncthreads();
         const uint32_t nc = s_ncand;
+        const bool full_now = s_full != 0;
+        __syncthreads();  // every warp has read the counter before anyone appends to it again (uniform decision below)
         const bool last = base + PER_ROUND >= d_hi;
-        if (nc + PER_ROUND > EXACT_CAND || !s_full || last) {  // drain (uniform decision)
+        if (nc + PER_ROUND > EXACT_CAND || !full_now || last) {  // drain (uniform decision)
             if (warp == 0) {
                 for (uint32_t i0 = 0; i0 < nc; i0 += 32) {
                     const uint32_t i = i0 + lane;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(EXACT_THREADS, 1) k_exact_partial(const ExactA
 }
 
 // one warp per query: merge the per-segment partial top-k lists, map keys to doc ids
-__global__ void __launch_bounds__(32) k_exact_merge(const ExactArgs a, const void*, float* out_scores,
+static __global__ void __launch_bounds__(32) k_exact_merge(const ExactArgs a, const void*, float* out_scores,
                                                     uint32_t* out_counts, uint64_t* out_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* heap_s = reinterpret_cast<float*>(smem_raw);

@@ -1,4 +1,5 @@
 #include "search_kernels.cuh"
+#include "exact.cuh"
 namespace sgpu {
 kern_t pick_rec16(QueryKind q, bool small_k) {
     switch (q) {
@@ -8,5 +9,8 @@ kern_t pick_rec16(QueryKind q, bool small_k) {
         case Q_RANK: return SGPU_K(256, 4, RankQuery, Rec16);
         default: return nullptr;
     }
+}
+exact_t pick_exact_rec16(bool dense) {
+    return dense ? (exact_t)k_exact_partial<DenseQuery, Rec16> : (exact_t)k_exact_partial<SortedQuery, Rec16>;
 }
 }  // namespace sgpu

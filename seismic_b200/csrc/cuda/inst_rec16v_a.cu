@@ -1,5 +1,6 @@
 #include "../../../include/seismic_b200.h"
 #include "search_kernels.cuh"
+#include "exact.cuh"
 namespace sgpu {
 kern_t pick_rec16v_b(uint32_t value_kind, QueryKind q, bool small_k);
 kern_t pick_rec16v(uint32_t value_kind, QueryKind q, bool small_k) {
@@ -9,6 +10,14 @@ kern_t pick_rec16v(uint32_t value_kind, QueryKind q, bool small_k) {
         case SGPU_VAL_BF16: return s ? SGPU_K(256, 4, SortedQuery, Rec16V2<1>) : SGPU_K(256, 4, ByteQuery, Rec16V2<1>);
         case SGPU_VAL_FIXEDU16: return s ? SGPU_K(256, 4, SortedQuery, Rec16V2<4>) : SGPU_K(256, 4, ByteQuery, Rec16V2<4>);
         default: return pick_rec16v_b(value_kind, q, small_k);
+    }
+}
+exact_t pick_exact_rec16v_b(uint32_t value_kind);
+exact_t pick_exact_rec16v(uint32_t value_kind) {
+    switch (value_kind) {
+        case SGPU_VAL_BF16: return (exact_t)k_exact_partial<SortedQuery, Rec16V2<1>>;
+        case SGPU_VAL_FIXEDU16: return (exact_t)k_exact_partial<SortedQuery, Rec16V2<4>>;
+        default: return pick_exact_rec16v_b(value_kind);
     }
 }
 }  // namespace sgpu

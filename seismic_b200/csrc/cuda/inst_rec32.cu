@@ -1,4 +1,5 @@
 #include "search_kernels.cuh"
+#include "exact.cuh"
 namespace sgpu {
 kern_t pick_rec32(QueryKind q, bool small_k) {
     switch (q) {
@@ -7,4 +8,5 @@ kern_t pick_rec32(QueryKind q, bool small_k) {
         default: return nullptr;
     }
 }
+exact_t pick_exact_rec32() { return (exact_t)k_exact_partial<SortedQuery, Rec32>; }
 }  // namespace sgpu

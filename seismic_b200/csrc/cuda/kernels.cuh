@@ -162,42 +162,73 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route(Scratch sc, uint32_t nq
 }
 
 // ------------------------------------------------------------------------------------------
-// k_est: Loop A.  One warp per (query, term).  est[s] accumulates, for the query components present
+// k_est: Loop A.  One CTA (4 warps) per (query, term).  est[s] accumulates, for the query components present
 // in the list's summaries IN ASCENDING COMPONENT ORDER, ((code * quant[s]) + min[s]) * qv with four
 // separate roundings (Rust does not contract to FMA).
 //
-// The addends do not depend on the accumulation order, only the additions do.  So a batch of up to 64 query
-// components is handled in three lane-parallel steps: (1) every lane binary-searches its component(s) in the
-// list's sorted summary components and fetches the run bounds; (2) the runs of all matched components are
-// laid end to end (warp prefix sum) and the lanes walk that flat entry list — every global load of the batch
-// (entry ids, codes, quants, mins) is independent of every other, so the memory latency is paid once per 32
-// entries instead of once per component — and stage (block id, addend) pairs in shared memory; (3) the staged
-// pairs are added to the accumulators component by component (a summary id occurs at most once per component,
-// so the lanes of one component never collide; components are separated by __syncwarp()).
-// The accumulators live in shared memory when the list has <= EST_SMEM blocks, else directly in the
-// global scratch (same algorithm, L2-coherent accesses).
+// A task touches a few thousand summary entries (the list's own component alone occurs in almost every block
+// summary).  The addends do not depend on the accumulation order, only the additions do, so up to 128 query components
+// are handled in three steps: (1) every thread searches one component in the list's sorted summary components (9-ary
+// search: eight independent pivot loads per step, four dependent steps for 4 000 components instead of twelve) and
+// fetches the run bounds; a block-wide scan lays the runs of the matched components end to end; (2) the threads walk
+// that flat entry list four positions at a time — entry ids and codes are independent streaming loads, the per-block
+// quant / min come from a shared-memory copy made up front, so one memory latency covers 512 entries — and stage
+// (block id, addend) pairs in shared memory; (3) the staged pairs are added run by run (= component by component,
+// ascending) by the whole CTA with a barrier between runs (a summary id occurs at most once per component, so the
+// threads of one step never collide).
+// Lists with more than EST_SMEM blocks keep quant / min / accumulators in global memory (same algorithm).
 // ------------------------------------------------------------------------------------------
-constexpr int EST_WARPS = 4;
-constexpr int EST_SMEM = 1024;   // blocks per warp kept in shared memory (4 x 4 KB); larger lists accumulate in global
-constexpr int EST_STAGE = 512;   // staged (block id, addend) pairs per warp
+constexpr int EST_THREADS = 128;
+constexpr int EST_SMEM = 1024;   // blocks whose quant / min / accumulator live in shared memory
+constexpr int EST_STAGE = 2048;  // staged (block id, addend) pairs per pass
+constexpr int EST_QB = EST_THREADS;  // query components per batch (one per thread)
 
-__global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc) {
-    __shared__ float s_est[EST_WARPS][EST_SMEM];
-    __shared__ float s_add[EST_WARPS][EST_STAGE];
-    __shared__ uint16_t s_blk[EST_WARPS][EST_STAGE];
-    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t task = blockIdx.x * EST_WARPS + w;
+// lower_bound(a[0, n), c) with eight independent probes per step
+__device__ __forceinline__ uint32_t lower_bound9(const uint32_t* __restrict__ a, uint32_t n, uint32_t c) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 8) {
+        const uint32_t st = (hi - lo + 8) / 9;  // nine pieces of st elements; probe the last element of the first eight
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t at = lo + (k + 1) * st - 1;
+            v[k] = at < hi ? __ldg(a + at) : 0xffffffffu;
+        }
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cnt += v[k] < c;
+        lo += cnt * st;
+        hi = min(hi, lo + st);
+    }
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = lo + k < hi ? __ldg(a + lo + k) : 0xffffffffu;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cnt += v[k] < c;
+    return lo + cnt;
+}
+
+__global__ void __launch_bounds__(EST_THREADS) k_est(DevIndex ix, Batch b, Scratch sc) {
+    __shared__ float s_acc[EST_SMEM], s_quant[EST_SMEM], s_min[EST_SMEM];
+    __shared__ float s_add[EST_STAGE];
+    __shared__ uint16_t s_blk[EST_STAGE];
+    __shared__ uint32_t s_off[EST_QB + 1];  // first flat position of every component's run (exclusive scan)
+    __shared__ uint32_t s_e0[EST_QB];
+    __shared__ float s_qv[EST_QB];
+    __shared__ uint32_t s_run[EST_QB];      // the batch's non-empty runs, in component order
+    __shared__ uint8_t s_own[EST_STAGE / 32];  // owner (component slot) of every 32nd flat position of the pass
+    __shared__ uint32_t s_wtot[EST_THREADS / 32], s_wcnt[EST_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t task = blockIdx.x;
     const uint32_t q = task / sc.cut_eff, t = task % sc.cut_eff;
-    if (q >= b.nq || t >= sc.nterms[q]) return;
+    if (q >= b.nq || t >= sc.nterms[q]) return;  // CTA-uniform
     const uint32_t l = sc.terms[(uint64_t)q * sc.cut_eff + t];
     const ListHdr h = ix.lists[l];
     const uint32_t B = h.n_blk;
     float* g_est = sc.est + ((uint64_t)q * sc.cut_eff + t) * sc.est_stride;
     const bool in_smem = B <= EST_SMEM;
-    float* acc = in_smem ? s_est[w] : g_est;
-    for (uint32_t i = lane; i < B; i += 32) acc[i] = 0.f;
-    __syncwarp();
-    if (!in_smem) __threadfence_block();
+    float* acc = in_smem ? s_acc : g_est;
     const uint64_t o = b.q_off[b.q_base + q];
     const uint32_t n = (uint32_t)(b.q_off[b.q_base + q + 1] - o);
     const uint32_t* scomp = ix.sc_comp + h.sc_base;
@@ -206,115 +237,111 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Sc
     const uint8_t* ec = ix.ent_code + h.ent_base;
     const float* mins = ix.blk_min + h.blk_base;
     const float* quants = ix.blk_quant + h.blk_base;
-    float* st_add = s_add[w];
-    uint16_t* st_blk = s_blk[w];
-    for (uint32_t base = 0; base < n; base += 64) {
-        // ---- (1) lane handles query components base + 2 * lane and base + 2 * lane + 1 (ascending across lanes)
-        uint32_t e0[2] = {0, 0}, len[2] = {0, 0};
-        float qv[2] = {0.f, 0.f};
-        uint32_t lo[2] = {0, 0}, hi[2] = {0, 0}, c[2] = {0, 0};
-        bool want[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const uint32_t i = base + 2 * lane + u;
-            want[u] = false;
-            if (i < n) {
-                c[u] = b.q_comps[o + i];
-                qv[u] = b.q_vals[o + i];
-                want[u] = !(i > 0 && b.q_comps[o + i - 1] == c[u]);  // the merge consumes the first duplicate only
-                hi[u] = want[u] ? h.n_sc : 0u;
-            }
-        }
-        while (__any_sync(0xffffffffu, lo[0] < hi[0] || lo[1] < hi[1])) {  // the two searches run interleaved
-            uint32_t mid[2], v[2] = {0, 0};
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                mid[u] = (lo[u] + hi[u]) >> 1;
-                if (lo[u] < hi[u]) v[u] = __ldg(scomp + mid[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (lo[u] < hi[u]) {
-                    if (v[u] < c[u]) lo[u] = mid[u] + 1;
-                    else hi[u] = mid[u];
+    for (uint32_t i = tid; i < B; i += EST_THREADS) {
+        acc[i] = 0.f;
+        if (in_smem) s_quant[i] = __ldg(quants + i), s_min[i] = __ldg(mins + i);
+    }
+    for (uint32_t base = 0; base < n; base += EST_QB) {
+        // ---- (1) one query component per thread
+        const uint32_t i = base + tid;
+        uint32_t e0 = 0, len = 0;
+        float qv = 0.f;
+        if (i < n) {
+            const uint32_t c = b.q_comps[o + i];
+            qv = b.q_vals[o + i];
+            if (!(i > 0 && b.q_comps[o + i - 1] == c)) {  // the merge consumes the first duplicate only
+                const uint32_t lo = lower_bound9(scomp, h.n_sc, c);
+                if (lo < h.n_sc && __ldg(scomp + lo) == c) {
+                    e0 = __ldg(run + lo);
+                    len = __ldg(run + lo + 1) - e0;
                 }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (want[u] && lo[u] < h.n_sc && __ldg(scomp + lo[u]) == c[u]) {
-                e0[u] = __ldg(run + lo[u]);
-                len[u] = __ldg(run + lo[u] + 1) - e0[u];
             }
-        // ---- flat entry list of the batch: exclusive prefix sum of the run lengths (slot 2 * lane + u)
-        const uint32_t mine = len[0] + len[1];
-        uint32_t incl = mine;
+        }
+        // block-wide exclusive scans of len (flat positions) and of (len > 0) (run list)
+        uint32_t incl = len, cinc = len ? 1u : 0u;
 #pragma unroll
         for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft);
-            if (lane >= (uint32_t)sft) incl += up;
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft), uc = __shfl_up_sync(0xffffffffu, cinc, sft);
+            if (lane >= (uint32_t)sft) incl += up, cinc += uc;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t off0 = incl - mine, off1 = off0 + len[0];  // first flat position of the lane's two runs
+        __syncthreads();  // previous batch's step (3) is done with s_off / s_run; the zeroing above is visible
+        if (lane == 31) s_wtot[warp] = incl, s_wcnt[warp] = cinc;
+        __syncthreads();
+        uint32_t woff = 0, wcnt = 0, total = 0, n_runs = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < EST_THREADS / 32; ++w) {
+            if (w < warp) woff += s_wtot[w], wcnt += s_wcnt[w];
+            total += s_wtot[w], n_runs += s_wcnt[w];
+        }
+        s_off[tid] = woff + incl - len;
+        s_e0[tid] = e0;
+        s_qv[tid] = qv;
+        if (len) s_run[wcnt + cinc - 1] = tid;
+        if (tid == 0) s_off[EST_QB] = total;
+        __syncthreads();
         for (uint32_t w0 = 0; w0 < total; w0 += EST_STAGE) {
             const uint32_t w1 = min(total, w0 + EST_STAGE);
-            // ---- (2) stage the addends of flat positions [w0, w1)
-            for (uint32_t p0 = w0; p0 < w1; p0 += 32) {
-                const uint32_t p = p0 + lane;
-                const bool act = p < w1;
-                // owner = last lane whose first position is <= p (lanes without entries share their successor's)
+            // owner of every 32nd position: last component slot whose first position is <= p
+            for (uint32_t g = tid; g * 32 < w1 - w0; g += EST_THREADS) {
+                const uint32_t p = w0 + g * 32;
                 uint32_t j = 0;
 #pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const uint32_t cand = j + step;
-                    const uint32_t oc = __shfl_sync(0xffffffffu, off0, cand & 31);
-                    if (cand < 32 && oc <= p) j = cand;
-                }
-                const uint32_t j_off0 = __shfl_sync(0xffffffffu, off0, j), j_off1 = __shfl_sync(0xffffffffu, off1, j);
-                const uint32_t j_e0 = __shfl_sync(0xffffffffu, e0[0], j), j_e1 = __shfl_sync(0xffffffffu, e0[1], j);
-                const float j_q0 = __shfl_sync(0xffffffffu, qv[0], j), j_q1 = __shfl_sync(0xffffffffu, qv[1], j);
-                if (act) {
-                    const bool second = p >= j_off1;
-                    const uint32_t e = second ? j_e1 + (p - j_off1) : j_e0 + (p - j_off0);
-                    const float wq = second ? j_q1 : j_q0;
-                    const uint32_t s = __ldg(eb + e);
-                    const float code = (float)__ldg(ec + e);
-                    const float deq = __fadd_rn(__fmul_rn(code, __ldg(quants + s)), __ldg(mins + s));
-                    st_blk[p - w0] = (uint16_t)s;
-                    st_add[p - w0] = __fmul_rn(deq, wq);
-                }
+                for (int step = EST_QB / 2; step > 0; step >>= 1)
+                    if (s_off[j + step] <= p) j += step;
+                s_own[g] = (uint8_t)j;
             }
-            __syncwarp();
-            // ---- (3) add, one component (= one run) at a time, in ascending component order
-            // slot order is (lane 0, u 0), (lane 0, u 1), (lane 1, u 0), ...: walk the lanes once, u = 0 then u = 1
-            uint32_t m0 = __ballot_sync(0xffffffffu, len[0] > 0 && off0 < w1 && off0 + len[0] > w0);
-            uint32_t m1 = __ballot_sync(0xffffffffu, len[1] > 0 && off1 < w1 && off1 + len[1] > w0);
-            uint32_t mm = m0 | m1;
-            while (mm) {
-                const int src = __ffs(mm) - 1;
-                mm &= mm - 1;
+            __syncthreads();
+            // ---- (2) stage the addends of flat positions [w0, w1), four independent positions per thread and step
+            for (uint32_t p0 = w0; p0 < w1; p0 += 4 * EST_THREADS) {
+                uint32_t pp[4], ee[4], ss[4];
+                float wq[4], code[4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (!(((u ? m1 : m0) >> src) & 1u)) continue;  // warp-uniform
-                    const uint32_t r0 = __shfl_sync(0xffffffffu, u ? off1 : off0, src);
-                    const uint32_t r1 = r0 + __shfl_sync(0xffffffffu, len[u], src);
-                    const uint32_t a0 = max(r0, w0), a1 = min(r1, w1);
-                    for (uint32_t p = a0 + lane; p < a1; p += 32) {
-                        const uint32_t s = st_blk[p - w0];
-                        const float add = st_add[p - w0];
-                        if (in_smem) {
-                            acc[s] = __fadd_rn(acc[s], add);
-                        } else {
-                            const float cur = __ldcg(acc + s);
-                            __stcg(acc + s, __fadd_rn(cur, add));
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    pp[u] = p0 + u * EST_THREADS + tid;
+                    if (pp[u] < w1) {
+                        uint32_t j = s_own[(pp[u] - w0) >> 5];
+                        while (s_off[j + 1] <= pp[u]) ++j;  // j + 1 <= EST_QB: s_off[EST_QB] = total > p
+                        ee[u] = s_e0[j] + (pp[u] - s_off[j]);
+                        wq[u] = s_qv[j];
                     }
-                    __syncwarp();
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (pp[u] < w1) ss[u] = __ldg(eb + ee[u]), code[u] = (float)__ldg(ec + ee[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (pp[u] < w1) {
+                        const float qn = in_smem ? s_quant[ss[u]] : __ldg(quants + ss[u]);
+                        const float mn = in_smem ? s_min[ss[u]] : __ldg(mins + ss[u]);
+                        s_blk[pp[u] - w0] = (uint16_t)ss[u];
+                        s_add[pp[u] - w0] = __fmul_rn(__fadd_rn(__fmul_rn(code[u], qn), mn), wq[u]);
+                    }
+            }
+            __syncthreads();
+            // ---- (3) add, one run (= one component) at a time in ascending component order
+            for (uint32_t r = 0; r < n_runs; ++r) {
+                const uint32_t j = s_run[r];
+                const uint32_t r0 = s_off[j], r1 = s_off[j + 1];
+                if (r1 <= w0 || r0 >= w1) continue;  // run outside this pass (CTA-uniform)
+                const uint32_t a0 = max(r0, w0), a1 = min(r1, w1);
+                for (uint32_t p = a0 + tid; p < a1; p += EST_THREADS) {
+                    const uint32_t s = s_blk[p - w0];
+                    const float add = s_add[p - w0];
+                    if (in_smem) {
+                        acc[s] = __fadd_rn(acc[s], add);
+                    } else {
+                        const float cur = __ldcg(acc + s);
+                        __stcg(acc + s, __fadd_rn(cur, add));
+                    }
+                }
+                __syncthreads();
             }
         }
     }
-    if (in_smem)
-        for (uint32_t i = lane; i < B; i += 32) g_est[i] = acc[i];
+    if (in_smem) {
+        __syncthreads();
+        for (uint32_t i = tid; i < B; i += EST_THREADS) g_est[i] = acc[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

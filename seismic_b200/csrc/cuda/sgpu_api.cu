@@ -612,7 +612,7 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         pd.launches += 2;
         CK(cudaEventRecord(ix->ev[3], st));
         const uint64_t tasks = (uint64_t)n * cut_eff;
-        k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);
+        k_est<<<(unsigned)tasks, EST_THREADS, 0, st>>>(ix->ix, b, sc);
         CK(cudaGetLastError());
         ++pd.launches;
         if (ad.first_sorted) {
@@ -877,8 +877,8 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
         shost::set_error("sgpu_exact_search: bad argument");
         return SGPU_EINVAL;
     }
-    if (ix->ix.comp32 || ix->ix.value_kind != SGPU_VAL_F16) {
-        shost::set_error("sgpu_exact_search: only available for u16/f16 indexes");
+    if (ix->ix.vbyte) {
+        shost::set_error("sgpu_exact_search: not available for DotVByte indexes (the reference has no FlatIndex over them)");
         return SGPU_EUNSUPPORTED;
     }
     CK(cudaSetDevice(ix->device));
@@ -886,12 +886,15 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
     if (nq == 0) return SGPU_OK;
     const uint64_t nnz = q->offsets[nq];
     cudaStream_t st = ix->stream;
-    for (uint64_t i = 0; i < nq; ++i)
+    uint64_t max_nnz = 0;
+    for (uint64_t i = 0; i < nq; ++i) {
+        max_nnz = std::max(max_nnz, q->offsets[i + 1] - q->offsets[i]);
         for (uint64_t j = q->offsets[i]; j < q->offsets[i + 1]; ++j)
             if (q->comps[j] >= ix->ix.dim || (j > q->offsets[i] && q->comps[j] < q->comps[j - 1])) {
                 shost::set_error("Query components must be sorted in ascending order and be < dim");
                 return SGPU_EINVAL;
             }
+    }
     CK(ix->d_qoff.ensure((nq + 1) * 8));
     CK(ix->d_qcomps.ensure(std::max<size_t>(nnz * 4, 4)));
     CK(ix->d_qvals.ensure(std::max<size_t>(nnz * 4, 4)));
@@ -921,18 +924,33 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
     ea.k = k;
     ea.seg_docs = seg_docs;
     ea.n_seg = n_seg;
-    ea.qd_words = (ix->ix.dim + 31u) & ~31u;
+    ea.chunk_units = ix->ix.rec_chunk_units;
+    ea.value_scale = ix->ix.value_scale;
     ea.part_keys = part_keys.as<uint32_t>();
     ea.part_scores = part_scores.as<float>();
-    const size_t smem = (size_t)ea.qd_words * 4 + 2 * (size_t)((k + 3) & ~3u) * 4 + EXACT_CAND * 8;
+    // dense f32 query for the u16/f16 layout when the vocabulary fits shared memory, else the sorted query (any length)
+    const size_t tail = 2 * (size_t)((k + 3) & ~3u) * 4 + EXACT_CAND * 8 + 32;
+    const uint32_t vkind = ix->ix.value_kind;
+    const bool plain16 = !ix->ix.comp32 && vkind == SGPU_VAL_F16;
+    const uint32_t dense_words = (ix->ix.dim + 31u) & ~31u;
+    const bool dense = plain16 && (size_t)dense_words * 4 + tail + 1024 <= ix->smem_optin;
+    ea.qd_words = dense ? dense_words : (uint32_t)std::max<uint64_t>(max_nnz, 1);
+    const size_t smem = (dense ? (size_t)ea.qd_words * 4 : (size_t)ea.qd_words * 8 + 16) + tail;
     if (smem + 1024 > ix->smem_optin) {
-        shost::set_error("dense query does not fit in shared memory");
+        shost::set_error("sgpu_exact_search: a query does not fit in shared memory");
         return SGPU_EUNSUPPORTED;
     }
-    CK(cudaFuncSetAttribute(k_exact_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    exact_t ke = plain16 ? pick_exact_rec16(dense)
+                         : (ix->ix.comp32 ? (vkind == SGPU_VAL_F16 ? pick_exact_rec32() : pick_exact_rec32v(vkind))
+                                          : pick_exact_rec16v(vkind));
+    if (!ke) {
+        shost::set_error("sgpu_exact_search: no kernel for this index layout");
+        return SGPU_EUNSUPPORTED;
+    }
+    CK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(ix->ev[0], st));
     const uint64_t n_cta = (uint64_t)nq * n_seg;
-    k_exact_partial<<<(unsigned)n_cta, EXACT_THREADS, smem, st>>>(ea);
+    ke<<<(unsigned)n_cta, EXACT_THREADS, smem, st>>>(ea);
     CK(cudaGetLastError());
     k_exact_merge<<<(unsigned)nq, 32, 2 * (size_t)((k + 3) & ~3u) * 4, st>>>(
         ea, nullptr, ix->d_out_scores.as<float>(), ix->d_out_counts.as<uint32_t>(),

@@ -99,7 +99,14 @@ int shost_index_convert_dotvbyte(const ShostIndex* idx, ShostIndex** out) {
     return convert_dotvbyte(*idx, out);
 }
 int shost_index_save(const ShostIndex* idx, const char* path) { return save_index(*idx, path); }
-int shost_index_load(const char* path, ShostIndex** out) { return load_index(path, out); }
+int shost_index_load(const char* path, ShostIndex** out) {
+    try {
+        return load_index(path, out);
+    } catch (const std::bad_alloc&) {
+        set_error("out of host memory");
+        return SGPU_ENOMEM;
+    }
+}
 void shost_index_destroy(ShostIndex* idx) { delete idx; }
 int shost_index_view(const ShostIndex* idx, SgpuIndexView* out) {
     fill_view(*idx, out);

@@ -30,7 +30,11 @@ static const char kMagic[8] = {'S', 'E', 'I', 'S', 'B', '2', '0', '0'};
 static const uint64_t kHeaderFixed = 120;
 
 int save_index(const ShostIndex& idx, const char* path) {
-    FILE* fp = std::fopen(path, "wb");
+    // The sections of a loaded index point into an mmap of its file, possibly `path` itself: write a temporary file in
+    // the same directory and rename it over the target, so re-saving over the source is safe (as it is for the
+    // reference, which deserialises into owned memory) and a failed save never leaves a truncated index behind.
+    const std::string tmp = std::string(path) + ".tmp" + std::to_string((long)getpid());
+    FILE* fp = std::fopen(tmp.c_str(), "wb");
     if (!fp) { set_error(std::string("cannot open for writing: ") + path); return SGPU_EIO; }
     std::vector<uint8_t> hdr(kHeaderFixed + SEC_COUNT * 16, 0);
     std::memcpy(hdr.data(), kMagic, 8);
@@ -64,7 +68,12 @@ int save_index(const ShostIndex& idx, const char* path) {
         cur += idx.sec[s].bytes;
     }
     if (std::fclose(fp) != 0) ok = false;
-    if (!ok) { set_error(std::string("short write: ") + path); return SGPU_EIO; }
+    if (ok && std::rename(tmp.c_str(), path) != 0) ok = false;
+    if (!ok) {
+        std::remove(tmp.c_str());
+        set_error(std::string("short write: ") + path);
+        return SGPU_EIO;
+    }
     return SGPU_OK;
 }
 
@@ -104,7 +113,7 @@ int load_index(const char* path, ShostIndex** out) {
         uint64_t off, bytes;
         std::memcpy(&off, p + kHeaderFixed + s * 16, 8);
         std::memcpy(&bytes, p + kHeaderFixed + s * 16 + 8, 8);
-        if (off + bytes > (uint64_t)st.st_size) {
+        if (bytes > (uint64_t)st.st_size || off > (uint64_t)st.st_size - bytes) {  // no overflow in off + bytes
             delete idx;
             set_error(std::string("truncated index file: ") + path);
             return SGPU_EIO;
@@ -112,6 +121,46 @@ int load_index(const char* path, ShostIndex** out) {
         idx->sec[s].ptr = p + off;
         idx->sec[s].bytes = bytes;
     }
+    // Cross-check every section length against the header and the start arrays: a corrupt file must raise, not crash.
+    auto fail = [&](const char* what) {
+        delete idx;
+        set_error(std::string("corrupt index file (") + what + "): " + path);
+        return SGPU_EIO;
+    };
+    const uint64_t N = idx->n_docs, D = idx->dim;
+    if ((idx->comp_bits != 16 && idx->comp_bits != 32) || idx->value_kind > SGPU_VAL_DOTVBYTE) return fail("encoding");
+    if (N >= (1ull << 40) || D == 0 || D > (1ull << 32)) return fail("n_docs / dim");
+    auto& S = idx->sec;
+    if (S[SEC_FWD_OFFSETS].bytes != (N + 1) * 8) return fail("fwd_offsets");
+    for (int sid : {SEC_LIST_POST_START, SEC_LIST_BLK_START, SEC_LIST_SC_START, SEC_LIST_ENT_START})
+        if (S[sid].bytes != (D + 1) * 8) return fail("list start arrays");
+    const uint64_t* fo = S[SEC_FWD_OFFSETS].as<uint64_t>();
+    for (uint64_t d = 0; d < N; ++d)
+        if (fo[d] > fo[d + 1]) return fail("fwd_offsets not monotone");
+    const bool vb = idx->value_kind == SGPU_VAL_DOTVBYTE;
+    const uint64_t vbytes = idx->value_kind == SGPU_VAL_F32 ? 4 : (idx->value_kind == SGPU_VAL_FIXEDU8 ? 1 : 2);
+    if (vb) {
+        if (S[SEC_FWD_VALUES].bytes < fo[N] || S[SEC_FWD_NNZ].bytes != N * 2) return fail("DotVByte stream");
+    } else {
+        if (fo[N] != idx->nnz || S[SEC_FWD_COMPS].bytes != fo[N] * (idx->comp_bits / 8) ||
+            S[SEC_FWD_VALUES].bytes != fo[N] * vbytes)
+            return fail("forward index");
+    }
+    auto last = [&](int sid) { return S[sid].as<uint64_t>()[D]; };
+    auto monotone = [&](int sid) {
+        const uint64_t* a = S[sid].as<uint64_t>();
+        for (uint64_t l = 0; l < D; ++l)
+            if (a[l] > a[l + 1]) return false;
+        return a[0] == 0;
+    };
+    for (int sid : {SEC_LIST_POST_START, SEC_LIST_BLK_START, SEC_LIST_SC_START, SEC_LIST_ENT_START})
+        if (!monotone(sid)) return fail("list start arrays not monotone");
+    const uint64_t P = last(SEC_LIST_POST_START), TB = last(SEC_LIST_BLK_START), TSC = last(SEC_LIST_SC_START),
+                   TE = last(SEC_LIST_ENT_START);
+    if (S[SEC_POSTINGS].bytes != P * 8 || S[SEC_BLK_POST_OFF].bytes != (TB + D) * 4 || S[SEC_BLK_MIN].bytes != TB * 4 ||
+        S[SEC_BLK_QUANT].bytes != TB * 4 || S[SEC_SC_COMP].bytes != TSC * 4 || S[SEC_SC_RUN_OFF].bytes != (TSC + D) * 4 ||
+        S[SEC_ENT_BLK].bytes != TE * 2 || S[SEC_ENT_CODE].bytes != TE)
+        return fail("posting list sections");
     *out = idx;
     return SGPU_OK;
 }

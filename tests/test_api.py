@@ -180,3 +180,59 @@ def test_dataset_exact_search():
     res = ds.search("q", np.array(["t%d" % x for x in qc[0]], dtype=st), qv[0], 10)
     # exact top-10 over f16-rounded values; the fixture's exact list was computed the same way
     assert [d for _, _, d in res] == [TOY["doc_ids"][i] for i in TOY["exact_top10"][0]]
+
+
+@pytest.mark.gpu
+def test_dataset_lv_exact_search():
+    """SeismicDatasetLV (u32 components): the exact search works (it raised in round 1)."""
+    comps, vals, qc, qv = toy_arrays()
+    st = seismic.get_seismic_string()
+    ds = seismic.SeismicDatasetLV()
+    for i, (c, v) in enumerate(zip(comps, vals)):
+        ds.add_document(TOY["doc_ids"][i], np.array(["t%d" % x for x in c], dtype=st), v)
+    res = ds.search("q", np.array(["t%d" % x for x in qc[0]], dtype=st), qv[0], 10)
+    assert [d for _, _, d in res] == [TOY["doc_ids"][i] for i in TOY["exact_top10"][0]]
+
+
+def test_save_over_the_loaded_file_and_corrupt_files(tmp_path):
+    """An index loaded from a file (mmap) can be saved over that same file (the reference deserialises into owned memory,
+    so this is safe there); truncated / inconsistent files raise OSError instead of crashing."""
+    comps, vals, qc, qv = toy_arrays()
+    host = HostIndex.build(Dataset.from_lists(comps, vals, dim=TOY["dim"]))
+    path = str(tmp_path / "a.idx")
+    host.save(path)
+    loaded = HostIndex.load(path)
+    loaded.save(path)                       # used to SIGBUS: the target was truncated while it backed the sections
+    again = HostIndex.load(path)
+    assert again.len == host.len and again.nnz == host.nnz
+    assert np.array_equal(again.arrays()["postings"], host.arrays()["postings"])
+    del loaded, again
+    raw = bytearray(open(path, "rb").read())
+    open(str(tmp_path / "short.idx"), "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(OSError):
+        HostIndex.load(str(tmp_path / "short.idx"))
+    bad = bytearray(raw)
+    bad[24:32] = (10 ** 6).to_bytes(8, "little")   # n_docs inflated: sections no longer match the header
+    open(str(tmp_path / "bad.idx"), "wb").write(bad)
+    with pytest.raises(OSError):
+        HostIndex.load(str(tmp_path / "bad.idx"))
+    big = bytearray(raw)
+    big[120 + 8:120 + 16] = (2 ** 64 - 64).to_bytes(8, "little")   # section length that overflows off + bytes
+    open(str(tmp_path / "big.idx"), "wb").write(big)
+    with pytest.raises(OSError):
+        HostIndex.load(str(tmp_path / "big.idx"))
+
+
+def test_knn_graph_travels_with_the_index(tmp_path):
+    """The reference serialises `knn: Option<Knn>` inside the index (src/inverted_index.rs:38-52): save + load keeps it."""
+    comps, vals, qc, qv = toy_arrays()
+    Dataset.from_lists(comps, vals, dim=TOY["dim"]).write_bin(str(tmp_path / "documents.bin"))
+    idx = seismic.SeismicIndexRaw.build(str(tmp_path / "documents.bin"))
+    graph = (np.arange(20 * 3, dtype=np.uint64).reshape(20, 3) * 7) % 20
+    idx._host.set_knn(graph)
+    idx.save(str(tmp_path / "g"))
+    back = seismic.SeismicIndexRaw.load(str(tmp_path / "g.index.seismic"))
+    assert back.knn_len == 3 and np.array_equal(back._host.knn, graph)
+    idx._host.set_knn(None)
+    idx.save(str(tmp_path / "g"))             # saved again without a graph: no stale graph is picked up
+    assert seismic.SeismicIndexRaw.load(str(tmp_path / "g.index.seismic")).knn_len == 0

@@ -339,3 +339,16 @@ def test_full_scan_equals_exact(synth_pruned, gpu_pruned):
         for r in range(int(counts[i])):
             c, v = index.get_doc(int(ids[i, r]))
             assert abs(float(np.dot(dense[c].astype(np.float64), v.astype(np.float64))) - scores[i, r]) <= 1e-4 * max(1.0, abs(scores[i, r]))
+
+
+@pytest.mark.parametrize("comp_bits,value_kind,dim", [(32, N.VAL_F16, 120000), (32, N.VAL_FIXEDU8, 90000),
+                                                     (16, N.VAL_BF16, 3000), (16, N.VAL_F16, 60000)])
+def test_exact_search_other_layouts(oracle_mod, comp_bits, value_kind, dim):
+    """Brute-force top-k (FlatIndex stand-in, src/inverted_index_wrapper.rs:721-742) on u32 / non-f16 layouts and on a
+    u16 vocabulary whose dense query does not fit shared memory (sorted-query kernel)."""
+    from conftest import build_synth
+    _, q, index = build_synth(12000, 40, dim=dim, comp_bits=comp_bits, n_postings=100, value_kind=value_kind)
+    g = GpuIndex(index, 0)
+    ref = oracle_mod.exact_search(index.view, q.offsets, q.comps, q.values, 10)
+    got = g.exact_search(q.offsets, q.comps, q.values, 10)
+    assert_same(got, ref, f"exact comp_bits={comp_bits} value_kind={value_kind}")
