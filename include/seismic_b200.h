@@ -186,6 +186,27 @@ int sgpu_index_set_option(SgpuIndex* index, const char* name, int64_t value);
 int sgpu_exact_search(SgpuIndex* index, const SgpuQueryBatch* queries, uint32_t k, uint64_t* out_ids,
                       float* out_scores, uint32_t* out_counts, float* ms_kernel);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: the index replicated on several devices of one box, ONE batch split across them (the
+ * reference's own parallelism is rayon over the queries of one batch_search call, src/pylib/mod.rs:629-652).
+ * Single process, no Python / torch needed: one SgpuIndex per device, the query batch cut into contiguous ranges,
+ * every device searches its range on its own stream, and the result tuples are gathered on the first device with ONE
+ * fused NCCL group of send/recv pairs over NVLink (ncclCommInitAll; libnccl.so.2 is opened at run time), then copied
+ * to the caller's host buffers.  Results are in input order and identical to a single-device call.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct SgpuGroup SgpuGroup;
+/* devices[n_devices]: CUDA ordinals (distinct); devices[0] receives the gather. */
+int sgpu_group_create(const SgpuIndexView* view, const int* devices, int n_devices, SgpuGroup** out);
+void sgpu_group_destroy(SgpuGroup* group);
+int sgpu_group_size(const SgpuGroup* group);
+/* kNN graph on every replica (see sgpu_index_set_knn). */
+int sgpu_group_set_knn(SgpuGroup* group, const uint64_t* neighbours, uint32_t knn_dim);
+/* Same contract as sgpu_batch_search (host buffers).  stats: device-side timings of devices[0]'s share; ms_gather
+ * (optional, may be NULL): device time of the NCCL gather on devices[0]. */
+int sgpu_group_batch_search(SgpuGroup* group, const SgpuQueryBatch* queries, const SgpuSearchParams* params,
+                            uint64_t* out_ids, float* out_scores, uint32_t* out_counts, SgpuSearchStats* stats,
+                            float* ms_gather);
+
 const char* sgpu_last_error(void);
 /* "seismic_b200 <version> sm_100a" */
 const char* sgpu_version(void);

@@ -247,28 +247,31 @@ float doc_score_t(const SgpuIndexView& v, const float* q, uint64_t start, uint32
 constexpr uint32_t VB_UNIT = 16;
 inline uint32_t vb_record_bytes(const SgpuIndexView& v, uint64_t start, uint32_t len) {
     const uint8_t* rec = (const uint8_t*)v.fwd_values + start * VB_UNIT;
-    const uint32_t nch = (len + 7) >> 3, nr = (nch + 7) >> 3;
-    const uint8_t* rounds = rec + 16ull * nch;
-    uint32_t bytes = 16 * nch + 16 * nr;
-    for (uint32_t m = 0; m < nch; ++m) bytes += __builtin_popcount(rounds[16 * (m >> 3) + (m & 7)]);
+    const uint32_t nch = (len + 7) >> 3;
+    const uint8_t* cum = rec + 16ull * nch;
+    const uint8_t* exc = cum + 2ull * nch;
+    uint32_t bytes = 16 * nch + 2 * nch + nch;
+    for (uint32_t m = 0; m < nch; ++m) {
+        uint16_t eo;
+        std::memcpy(&eo, cum + 2ull * m, 2);
+        bytes += __builtin_popcount(exc[eo]);
+    }
     return bytes;
 }
 template <int ORDER>
 float doc_score_vbyte(const SgpuIndexView& v, const float* q, uint64_t start, uint32_t len) {
     const uint8_t* rec = (const uint8_t*)v.fwd_values + start * VB_UNIT;
-    const uint32_t nch = (len + 7) >> 3, nr = (nch + 7) >> 3;
-    const uint8_t* rounds = rec + 16ull * nch;
-    const uint8_t* exc = rounds + 16ull * nr;
+    const uint32_t nch = (len + 7) >> 3;
+    const uint8_t* cum = rec + 16ull * nch;
+    const uint8_t* exc0 = cum + 2ull * nch;
     const float c24 = 5.9604644775390625e-08f;  // 2^-24
     float p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seq = 0.f;
     for (uint32_t m = 0; m < nch; ++m) {
         const uint8_t* fx = rec + 16ull * m;
-        const uint32_t ctrl = rounds[16 * (m >> 3) + (m & 7)];
-        if ((m & 7) == 0) {  // the round header's offset must agree with the running position
-            uint32_t eo;
-            std::memcpy(&eo, rounds + 16 * (m >> 3) + 8, 4);
-            exc = rounds + 16ull * nr + eo;
-        }
+        uint16_t eo;
+        std::memcpy(&eo, cum + 2ull * m, 2);
+        const uint8_t* exc = exc0 + eo;
+        const uint32_t ctrl = *exc++;
         uint32_t c = 0;
         for (uint32_t f = 0; f < 8; ++f) {
             uint32_t field = fx[f];

@@ -147,6 +147,12 @@ SYMBOLS = {
     "sgpu_index_set_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "sgpu_exact_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.c_uint32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_float)]),
+    "sgpu_group_create": (C.c_int, [C.POINTER(IndexView), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "sgpu_group_destroy": (None, [C.c_void_p]),
+    "sgpu_group_size": (C.c_int, [C.c_void_p]),
+    "sgpu_group_set_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sgpu_group_batch_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.POINTER(SearchParams), C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.POINTER(SearchStats), C.POINTER(C.c_float)]),
     "sgpu_last_error": (C.c_char_p, []),
     "sgpu_version": (C.c_char_p, []),
     "shost_default_config": (None, [C.POINTER(BuildConfig)]),

@@ -348,6 +348,51 @@ class GpuIndex:
         return ids, scores, counts
 
 
+class GpuGroup:
+    """The index replicated on several GPUs of one box; one batch is split across them and the result tuples are
+    gathered on the first device with one NCCL group (sgpu_group_*, single process — what a Rust host would call)."""
+
+    def __init__(self, host: HostIndex, devices: Sequence[int]):
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._h = C.c_void_p()
+        N.check(N.lib().sgpu_group_create(C.byref(host.view), devs, len(devices), C.byref(self._h)))
+        self.devices = list(devices)
+        self.last_stats: dict = {}
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            N.lib().sgpu_group_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __len__(self) -> int:
+        return int(N.lib().sgpu_group_size(self._h))
+
+    def set_knn(self, neighbours: Optional[np.ndarray]) -> None:
+        if neighbours is None:
+            N.check(N.lib().sgpu_group_set_knn(self._h, None, 0))
+            return
+        nb = np.ascontiguousarray(neighbours, dtype=np.uint64)
+        N.check(N.lib().sgpu_group_set_knn(self._h, N.ptr(nb), nb.shape[1]))
+
+    def batch_search(self, offsets, comps, values, k, query_cut, heap_factor, n_knn=0, first_sorted=True):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        comps = np.ascontiguousarray(comps, dtype=np.uint32)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        nq = len(offsets) - 1
+        ids = np.empty((nq, k), dtype=np.uint64)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.uint32)
+        qb = N.QueryBatch(nq, N.ptr(offsets), N.ptr(comps), N.ptr(values))
+        p = GpuIndex._params(k, query_cut, heap_factor, n_knn, first_sorted)
+        st = N.SearchStats()
+        ms = C.c_float()
+        N.check(N.lib().sgpu_group_batch_search(self._h, C.byref(qb), C.byref(p), N.ptr(ids), N.ptr(scores),
+                                                N.ptr(counts), C.byref(st), C.byref(ms)))
+        self.last_stats = st.as_dict()
+        self.last_stats["ms_gather"] = ms.value
+        return ids, scores, counts
+
+
 def recall_at_k(exact_ids: np.ndarray, exact_counts: np.ndarray, run_ids: np.ndarray, run_counts: np.ndarray) -> float:
     """accuracy@k = sum_q |gt_q ∩ run_q| / sum_q |gt_q| (reference scripts/run_experiments.py:287-309)."""
     hit = 0

@@ -162,41 +162,41 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route(Scratch sc, uint32_t nq
 }
 
 // ------------------------------------------------------------------------------------------
-// k_est: Loop A.  One CTA (4 warps) per (query, term).  est[s] accumulates, for the query components present
-// in the list's summaries IN ASCENDING COMPONENT ORDER, ((code * quant[s]) + min[s]) * qv with four
-// separate roundings (Rust does not contract to FMA).
+// k_est: Loop A.  One warp per (query, term), four independent warps per CTA.  est[s] accumulates, for the query
+// components present in the list's summaries IN ASCENDING COMPONENT ORDER, ((code * quant[s]) + min[s]) * qv with
+// four separate roundings (Rust does not contract to FMA).
 //
-// A task touches a few thousand summary entries (the list's own component alone occurs in almost every block
-// summary).  The addends do not depend on the accumulation order, only the additions do, so up to 128 query components
-// are handled in three steps: (1) every thread searches one component in the list's sorted summary components (9-ary
-// search: eight independent pivot loads per step, four dependent steps for 4 000 components instead of twelve) and
-// fetches the run bounds; a block-wide scan lays the runs of the matched components end to end; (2) the threads walk
-// that flat entry list four positions at a time — entry ids and codes are independent streaming loads, the per-block
-// quant / min come from a shared-memory copy made up front, so one memory latency covers 512 entries — and stage
-// (block id, addend) pairs in shared memory; (3) the staged pairs are added run by run (= component by component,
-// ascending) by the whole CTA with a barrier between runs (a summary id occurs at most once per component, so the
-// threads of one step never collide).
-// Lists with more than EST_SMEM blocks keep quant / min / accumulators in global memory (same algorithm).
+// A task touches one to a few thousand summary entries (the list's own component alone occurs in almost every block
+// summary) and is bound by dependent memory round trips, not by bytes.  The addends do not depend on the accumulation
+// order, only the additions do, so a batch of up to 64 query components is handled in three steps: (1) every lane
+// searches two components in the list's sorted summary components (5-ary search: four independent probes per step,
+// then one 8-element probe) and fetches the run bounds; a warp scan lays the runs of the matched components end to
+// end; (2) the lanes walk that flat entry list, EST_U positions per lane and step, all loads of a step issued before
+// the first use — one memory latency covers 32 * EST_U entries instead of one run — and stage (block id, addend)
+// pairs in shared memory; (3) the staged pairs are added run by run (= component by component, ascending; a summary id
+// occurs at most once per component, so the lanes of one step never collide), __syncwarp() between runs.
+// The accumulators live in shared memory when the list has <= EST_SMEM blocks, else in the global scratch.
 // ------------------------------------------------------------------------------------------
-constexpr int EST_THREADS = 128;
-constexpr int EST_SMEM = 1024;   // blocks whose quant / min / accumulator live in shared memory
-constexpr int EST_STAGE = 2048;  // staged (block id, addend) pairs per pass
-constexpr int EST_QB = EST_THREADS;  // query components per batch (one per thread)
+constexpr int EST_WARPS = 4;
+constexpr int EST_SMEM = 1024;  // blocks per warp kept in shared memory (4 KB); larger lists accumulate in global
+constexpr int EST_STAGE = 512;  // staged (block id, addend) pairs per warp and pass
+constexpr int EST_QB = 64;      // query components per batch (two per lane)
+constexpr int EST_U = 4;        // flat positions per lane and staging step
 
-// lower_bound(a[0, n), c) with eight independent probes per step
-__device__ __forceinline__ uint32_t lower_bound9(const uint32_t* __restrict__ a, uint32_t n, uint32_t c) {
+// lower_bound(a[0, n), c): four independent probes per step, one aligned-size probe of up to 8 elements at the end
+__device__ __forceinline__ uint32_t lower_bound5(const uint32_t* __restrict__ a, uint32_t n, uint32_t c) {
     uint32_t lo = 0, hi = n;
     while (hi - lo > 8) {
-        const uint32_t st = (hi - lo + 8) / 9;  // nine pieces of st elements; probe the last element of the first eight
-        uint32_t v[8];
+        const uint32_t st = (hi - lo + 4) / 5;  // five pieces of st elements; probe the last element of the first four
+        uint32_t v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
             const uint32_t at = lo + (k + 1) * st - 1;
             v[k] = at < hi ? __ldg(a + at) : 0xffffffffu;
         }
         uint32_t cnt = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cnt += v[k] < c;
+        for (int k = 0; k < 4; ++k) cnt += v[k] < c;
         lo += cnt * st;
         hi = min(hi, lo + st);
     }
@@ -209,124 +209,128 @@ __device__ __forceinline__ uint32_t lower_bound9(const uint32_t* __restrict__ a,
     return lo + cnt;
 }
 
-__global__ void __launch_bounds__(EST_THREADS) k_est(DevIndex ix, Batch b, Scratch sc) {
-    __shared__ float s_acc[EST_SMEM], s_quant[EST_SMEM], s_min[EST_SMEM];
-    __shared__ float s_add[EST_STAGE];
-    __shared__ uint16_t s_blk[EST_STAGE];
-    __shared__ uint32_t s_off[EST_QB + 1];  // first flat position of every component's run (exclusive scan)
-    __shared__ uint32_t s_e0[EST_QB];
-    __shared__ float s_qv[EST_QB];
-    __shared__ uint32_t s_run[EST_QB];      // the batch's non-empty runs, in component order
-    __shared__ uint8_t s_own[EST_STAGE / 32];  // owner (component slot) of every 32nd flat position of the pass
-    __shared__ uint32_t s_wtot[EST_THREADS / 32], s_wcnt[EST_THREADS / 32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t task = blockIdx.x;
+__global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc) {
+    __shared__ float s_est[EST_WARPS][EST_SMEM];
+    __shared__ float s_add[EST_WARPS][EST_STAGE];
+    __shared__ uint16_t s_blk[EST_WARPS][EST_STAGE];
+    __shared__ uint32_t s_off[EST_WARPS][EST_QB + 1];  // first flat position of every component's run (exclusive scan)
+    __shared__ uint32_t s_e0[EST_WARPS][EST_QB];
+    __shared__ float s_qv[EST_WARPS][EST_QB];
+    __shared__ uint8_t s_own[EST_WARPS][EST_STAGE / 32];  // owner (component slot) of every 32nd position of the pass
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t task = blockIdx.x * EST_WARPS + w;
     const uint32_t q = task / sc.cut_eff, t = task % sc.cut_eff;
-    if (q >= b.nq || t >= sc.nterms[q]) return;  // CTA-uniform
+    if (q >= b.nq || t >= sc.nterms[q]) return;  // warp-uniform; no block-wide barrier below
     const uint32_t l = sc.terms[(uint64_t)q * sc.cut_eff + t];
     const ListHdr h = ix.lists[l];
     const uint32_t B = h.n_blk;
     float* g_est = sc.est + ((uint64_t)q * sc.cut_eff + t) * sc.est_stride;
     const bool in_smem = B <= EST_SMEM;
-    float* acc = in_smem ? s_acc : g_est;
+    float* acc = in_smem ? s_est[w] : g_est;
+    for (uint32_t i = lane; i < B; i += 32) acc[i] = 0.f;
     const uint64_t o = b.q_off[b.q_base + q];
     const uint32_t n = (uint32_t)(b.q_off[b.q_base + q + 1] - o);
     const uint32_t* scomp = ix.sc_comp + h.sc_base;
+    const uint32_t* skip = ix.sc_skip + h.skip_base;
+    const uint32_t n_skip = (h.n_sc + 31) >> 5;
     const uint32_t* run = ix.sc_run_off + h.sc_base + l;
     const uint16_t* eb = ix.ent_blk + h.ent_base;
     const uint8_t* ec = ix.ent_code + h.ent_base;
     const float* mins = ix.blk_min + h.blk_base;
     const float* quants = ix.blk_quant + h.blk_base;
-    for (uint32_t i = tid; i < B; i += EST_THREADS) {
-        acc[i] = 0.f;
-        if (in_smem) s_quant[i] = __ldg(quants + i), s_min[i] = __ldg(mins + i);
-    }
+    uint32_t* off = s_off[w];
+    uint32_t* e0s = s_e0[w];
+    float* qvs = s_qv[w];
+    float* st_add = s_add[w];
+    uint16_t* st_blk = s_blk[w];
+    uint8_t* own = s_own[w];
+    __syncwarp();
+    if (!in_smem) __threadfence_block();
     for (uint32_t base = 0; base < n; base += EST_QB) {
-        // ---- (1) one query component per thread
-        const uint32_t i = base + tid;
-        uint32_t e0 = 0, len = 0;
-        float qv = 0.f;
-        if (i < n) {
-            const uint32_t c = b.q_comps[o + i];
-            qv = b.q_vals[o + i];
-            if (!(i > 0 && b.q_comps[o + i - 1] == c)) {  // the merge consumes the first duplicate only
-                const uint32_t lo = lower_bound9(scomp, h.n_sc, c);
-                if (lo < h.n_sc && __ldg(scomp + lo) == c) {
-                    e0 = __ldg(run + lo);
-                    len = __ldg(run + lo + 1) - e0;
+        // ---- (1) lane handles query components base + 2 * lane and base + 2 * lane + 1 (ascending across lanes)
+        uint32_t e0[2] = {0, 0}, len[2] = {0, 0};
+        float qv[2] = {0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t i = base + 2 * lane + u;
+            if (i < n) {
+                const uint32_t c = b.q_comps[o + i];
+                qv[u] = b.q_vals[o + i];
+                if (!(i > 0 && b.q_comps[o + i - 1] == c)) {  // the merge consumes the first duplicate only
+                    // directory first (the 40 searches of a task share its ~16 sectors), then one group of 32
+                    const uint32_t g = lower_bound5(skip, n_skip, c);
+                    const uint32_t glen = g < n_skip ? min(32u, h.n_sc - 32 * g) : 0u;
+                    const uint32_t lo = 32 * g + lower_bound5(scomp + 32 * g, glen, c);
+                    if (g < n_skip && lo < h.n_sc && __ldg(scomp + lo) == c) {
+                        e0[u] = __ldg(run + lo);
+                        len[u] = __ldg(run + lo + 1) - e0[u];
+                    }
                 }
             }
         }
-        // block-wide exclusive scans of len (flat positions) and of (len > 0) (run list)
-        uint32_t incl = len, cinc = len ? 1u : 0u;
+        // flat entry list of the batch: exclusive prefix sum of the run lengths (slot 2 * lane + u)
+        const uint32_t mine = len[0] + len[1];
+        uint32_t incl = mine;
 #pragma unroll
         for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft), uc = __shfl_up_sync(0xffffffffu, cinc, sft);
-            if (lane >= (uint32_t)sft) incl += up, cinc += uc;
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft);
+            if (lane >= (uint32_t)sft) incl += up;
         }
-        __syncthreads();  // previous batch's step (3) is done with s_off / s_run; the zeroing above is visible
-        if (lane == 31) s_wtot[warp] = incl, s_wcnt[warp] = cinc;
-        __syncthreads();
-        uint32_t woff = 0, wcnt = 0, total = 0, n_runs = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < EST_THREADS / 32; ++w) {
-            if (w < warp) woff += s_wtot[w], wcnt += s_wcnt[w];
-            total += s_wtot[w], n_runs += s_wcnt[w];
-        }
-        s_off[tid] = woff + incl - len;
-        s_e0[tid] = e0;
-        s_qv[tid] = qv;
-        if (len) s_run[wcnt + cinc - 1] = tid;
-        if (tid == 0) s_off[EST_QB] = total;
-        __syncthreads();
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        off[2 * lane] = incl - mine;
+        off[2 * lane + 1] = incl - mine + len[0];
+        e0s[2 * lane] = e0[0], e0s[2 * lane + 1] = e0[1];
+        qvs[2 * lane] = qv[0], qvs[2 * lane + 1] = qv[1];
+        if (lane == 0) off[EST_QB] = total;
+        __syncwarp();
         for (uint32_t w0 = 0; w0 < total; w0 += EST_STAGE) {
             const uint32_t w1 = min(total, w0 + EST_STAGE);
-            // owner of every 32nd position: last component slot whose first position is <= p
-            for (uint32_t g = tid; g * 32 < w1 - w0; g += EST_THREADS) {
-                const uint32_t p = w0 + g * 32;
+            // owner of every 32nd position of the pass: last slot whose first position is <= p
+            if (lane * 32 < w1 - w0) {
+                const uint32_t p = w0 + lane * 32;
                 uint32_t j = 0;
 #pragma unroll
                 for (int step = EST_QB / 2; step > 0; step >>= 1)
-                    if (s_off[j + step] <= p) j += step;
-                s_own[g] = (uint8_t)j;
+                    if (off[j + step] <= p) j += step;
+                own[lane] = (uint8_t)j;
             }
-            __syncthreads();
-            // ---- (2) stage the addends of flat positions [w0, w1), four independent positions per thread and step
-            for (uint32_t p0 = w0; p0 < w1; p0 += 4 * EST_THREADS) {
-                uint32_t pp[4], ee[4], ss[4];
-                float wq[4], code[4];
+            __syncwarp();
+            // ---- (2) stage the addends of flat positions [w0, w1)
+            for (uint32_t p0 = w0; p0 < w1; p0 += 32 * EST_U) {
+                uint32_t pp[EST_U], ee[EST_U], ss[EST_U];
+                float wq[EST_U], code[EST_U], qn[EST_U], mn[EST_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    pp[u] = p0 + u * EST_THREADS + tid;
+                for (int u = 0; u < EST_U; ++u) {
+                    pp[u] = p0 + u * 32 + lane;
                     if (pp[u] < w1) {
-                        uint32_t j = s_own[(pp[u] - w0) >> 5];
-                        while (s_off[j + 1] <= pp[u]) ++j;  // j + 1 <= EST_QB: s_off[EST_QB] = total > p
-                        ee[u] = s_e0[j] + (pp[u] - s_off[j]);
-                        wq[u] = s_qv[j];
+                        uint32_t j = own[(pp[u] - w0) >> 5];
+                        while (off[j + 1] <= pp[u]) ++j;  // off[EST_QB] = total > p ends the walk
+                        ee[u] = e0s[j] + (pp[u] - off[j]);
+                        wq[u] = qvs[j];
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < EST_U; ++u)
                     if (pp[u] < w1) ss[u] = __ldg(eb + ee[u]), code[u] = (float)__ldg(ec + ee[u]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < EST_U; ++u)
+                    if (pp[u] < w1) qn[u] = __ldg(quants + ss[u]), mn[u] = __ldg(mins + ss[u]);
+#pragma unroll
+                for (int u = 0; u < EST_U; ++u)
                     if (pp[u] < w1) {
-                        const float qn = in_smem ? s_quant[ss[u]] : __ldg(quants + ss[u]);
-                        const float mn = in_smem ? s_min[ss[u]] : __ldg(mins + ss[u]);
-                        s_blk[pp[u] - w0] = (uint16_t)ss[u];
-                        s_add[pp[u] - w0] = __fmul_rn(__fadd_rn(__fmul_rn(code[u], qn), mn), wq[u]);
+                        st_blk[pp[u] - w0] = (uint16_t)ss[u];
+                        st_add[pp[u] - w0] = __fmul_rn(__fadd_rn(__fmul_rn(code[u], qn[u]), mn[u]), wq[u]);
                     }
             }
-            __syncthreads();
-            // ---- (3) add, one run (= one component) at a time in ascending component order
-            for (uint32_t r = 0; r < n_runs; ++r) {
-                const uint32_t j = s_run[r];
-                const uint32_t r0 = s_off[j], r1 = s_off[j + 1];
-                if (r1 <= w0 || r0 >= w1) continue;  // run outside this pass (CTA-uniform)
+            __syncwarp();
+            // ---- (3) add, one run (= one component) at a time, in ascending component order
+            for (uint32_t j = 0; j < EST_QB; ++j) {
+                const uint32_t r0 = off[j], r1 = off[j + 1];
+                if (r1 <= w0 || r0 >= w1 || r0 == r1) continue;  // warp-uniform
                 const uint32_t a0 = max(r0, w0), a1 = min(r1, w1);
-                for (uint32_t p = a0 + tid; p < a1; p += EST_THREADS) {
-                    const uint32_t s = s_blk[p - w0];
-                    const float add = s_add[p - w0];
+                for (uint32_t p = a0 + lane; p < a1; p += 32) {
+                    const uint32_t s = st_blk[p - w0];
+                    const float add = st_add[p - w0];
                     if (in_smem) {
                         acc[s] = __fadd_rn(acc[s], add);
                     } else {
@@ -334,14 +338,13 @@ __global__ void __launch_bounds__(EST_THREADS) k_est(DevIndex ix, Batch b, Scrat
                         __stcg(acc + s, __fadd_rn(cur, add));
                     }
                 }
-                __syncthreads();
+                __syncwarp();
             }
         }
+        __syncwarp();
     }
-    if (in_smem) {
-        __syncthreads();
-        for (uint32_t i = tid; i < B; i += EST_THREADS) g_est[i] = acc[i];
-    }
+    if (in_smem)
+        for (uint32_t i = lane; i < B; i += 32) g_est[i] = acc[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -373,6 +376,8 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, S
         for (uint32_t i = threadIdx.x; i < n2; i += ORDER_THREADS)
             s_key[i] = i < B ? (((uint64_t)(~total_key(est[i])) << 32) | i) : ~0ull;
         __syncthreads();
+        // thread t owns elements t, t + 256, ...: for j < 32 both partners of an exchange belong to the same warp
+        // (same 32-aligned group of elements), so only the steps with j >= 32 need a block-wide barrier
         for (uint32_t ksz = 2; ksz <= n2; ksz <<= 1)
             for (uint32_t j = ksz >> 1; j > 0; j >>= 1) {
                 for (uint32_t i = threadIdx.x; i < n2; i += ORDER_THREADS) {
@@ -383,7 +388,8 @@ __global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, S
                         if ((a > c) == up) s_key[i] = c, s_key[p] = a;
                     }
                 }
-                __syncthreads();
+                if (j >= 32 || j == 1 && (ksz << 1) > 32) __syncthreads();  // also before the next step's wide exchange
+                else __syncwarp();
             }
         for (uint32_t i = threadIdx.x; i < B; i += ORDER_THREADS) emit(i, (uint32_t)(s_key[i] & 0xffffu));
     } else {
@@ -440,6 +446,17 @@ __global__ void k_knn_posts(const uint64_t* __restrict__ ids, uint64_t n, const 
 // ------------------------------------------------------------------------------------------
 // Image construction helpers (run once per index).
 // ------------------------------------------------------------------------------------------
+// directory of a list's sorted summary components: the last id of every group of 32 (one warp per list)
+__global__ void k_build_skip(const ListHdr* __restrict__ lists, uint32_t dim, const uint32_t* __restrict__ sc_comp,
+                             uint32_t* __restrict__ sc_skip) {
+    const uint32_t l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (l >= dim) return;
+    const ListHdr h = lists[l];
+    const uint32_t n_skip = (h.n_sc + 31) >> 5;
+    for (uint32_t i = threadIdx.x & 31; i < n_skip; i += 32)
+        sc_skip[h.skip_base + i] = sc_comp[h.sc_base + min(32 * i + 31, h.n_sc - 1)];
+}
+
 // one warp per document: element arrays -> 32-byte chunk records, tail padded with zeros
 __global__ void k_pack_records(const uint64_t* fwd_off, const uint16_t* comps, const uint16_t* vals,
                                const uint32_t* rec_start, uint64_t doc0, uint64_t n_docs_chunk, uint64_t elem0,

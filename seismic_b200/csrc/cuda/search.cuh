@@ -635,16 +635,16 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
 
 // ---- DotVByte records: gap-coded u16 components (1 or 2 bytes per gap) + u8 values --------
 // Format: csrc/host/build.cpp (convert_dotvbyte).  The posting's start field counts 16-byte units of the byte stream.
-// Per record: 16 bytes per chunk [8 low bytes of (first component, gap 1..7) | 8 codes], then 16 bytes per round of 8
-// chunks [8 control bytes | u32 offset of the round's exception bytes | 0], then the exception area (the high bytes that
-// exist).  lane8 decodes chunk lane8 of every round: one 128-bit load of its chunk, one 128-bit load of the round header
-// (the same address for the 8 lanes of the group), a popcount of the preceding control bytes, an unaligned 8-byte window
-// of the exception area (three aligned 32-bit loads + two funnel shifts), a 256-entry table of byte-permute selectors
-// that spreads the present high bytes to their fields, four byte-permutes that pair low and high bytes into u16 gaps, a
-// packed prefix sum — and the result is exactly a chunk of the plain layout (4 words of two u16 components, 4 words of
-// two f16 values), fed to the same lookup / multiply-add code.  A code byte c is read as the f16 SUBNORMAL c * 2^-24
-// (exact), so the f16 -> f32 conversion of the plain layout doubles as the integer -> float conversion; the factor
-// scale * 2^24 is applied once per document (oracle: doc_score_vbyte).
+// Per record: 16 bytes per chunk [8 low bytes of (first component, gap 1..7) | 8 codes], then a u16 per chunk = offset
+// of its exception group, then the exception groups [control byte | the high bytes that exist].  lane8 decodes chunk
+// lane8 of every round: one 128-bit load of its chunk, an unaligned 12-byte window of its exception group (three
+// aligned 32-bit loads; the group's offset was loaded one round ahead, so the loads of a round depend on nothing
+// loaded in that round), byte permutes that line the window up behind the control byte, a 256-entry table of
+// byte-permute selectors that spreads the present high bytes to their fields, four byte-permutes that pair low and
+// high bytes into u16 gaps, a packed prefix sum — and the result is exactly a chunk of the plain layout (4 words of
+// two u16 components, 4 words of two f16 values), fed to the same lookup / multiply-add code.  A code byte c is read
+// as the f16 SUBNORMAL c * 2^-24 (exact), so the f16 -> f32 conversion of the plain layout doubles as the integer ->
+// float conversion; the factor scale * 2^24 is applied once per document (oracle: doc_score_vbyte).
 struct RecVB {
     static constexpr bool VBYTE = true;
     static constexpr int UNIT_BYTES = 16;
@@ -654,9 +654,15 @@ struct is_vbyte { static constexpr bool value = false; };
 template <>
 struct is_vbyte<RecVB> { static constexpr bool value = true; };
 
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {  // selector nibbles must be 0..7
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // Table entry for control byte t (bit 7: the first component has a high byte, bit f-1: gap f has one).  The present
-// high bytes are consecutive in the exception window, first component first.  x = byte-permute selectors for the high
-// bytes of fields 0..3 (low half) and 4..7 (high half), y / z = masks clearing the absent ones.
+// high bytes are consecutive behind the control byte, first component first.  x / y = byte-permute selectors for the
+// high bytes of fields 0..3 / 4..7 out of the 8 bytes that follow the control byte, z / w = masks clearing the absent.
 __device__ __forceinline__ uint4 vb_lut_entry(uint32_t t) {
     uint32_t sel[2] = {0, 0}, msk[2] = {0, 0}, pos = 0;
 #pragma unroll
@@ -668,63 +674,69 @@ __device__ __forceinline__ uint4 vb_lut_entry(uint32_t t) {
             ++pos;
         }
     }
-    return make_uint4(sel[0] | (sel[1] << 16), msk[0], msk[1], pos);
+    return make_uint4(sel[0], sel[1], msk[0], msk[1]);
 }
 
-// one chunk of a DotVByte record -> the plain layout's (component words, value words)
-__device__ __forceinline__ void vb_decode(const uint8_t* __restrict__ rec, uint32_t nch, uint32_t m, uint32_t r,
-                                          uint32_t lane8, uint32_t pm0, uint32_t pm1, uint32_t lut_s, uint4& c, uint4& v,
+// one chunk of a DotVByte record -> the plain layout's (component words, value words).  `e` = address of the chunk's
+// exception group, `fx` = its 16 fixed bytes.
+__device__ __forceinline__ void vb_decode(const uint4 fx, const uint8_t* __restrict__ e, uint32_t lut_s, uint4& c, uint4& v,
                                           uint32_t& bytes) {
-    const uint32_t nr = (nch + 7) >> 3;
-    const uint4 fx = ld_stream(reinterpret_cast<const uint4*>(rec) + m);
-    const uint4 rh = ld_stream(reinterpret_cast<const uint4*>(rec) + nch + r);
-    const uint32_t ctrl = __byte_perm(rh.x, rh.y, lane8) & 0xffu;
-    const uint32_t pre = __popc(rh.x & pm0) + __popc(rh.y & pm1);  // exception bytes of the round's earlier chunks
-    const uint8_t* e = rec + 16u * (nch + nr) + rh.z + pre;
     const uint32_t* ew = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(e) & ~(uintptr_t)3);
-    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(e) & 3u) * 8;
+    const uint32_t a = (uint32_t)reinterpret_cast<uintptr_t>(e) & 3u;
     const uint32_t w0 = __ldg(ew), w1 = __ldg(ew + 1), w2 = __ldg(ew + 2);
-    const uint32_t X0 = __funnelshift_r(w0, w1, sh), X1 = __funnelshift_r(w1, w2, sh);
+    const uint32_t ctrl = prmt(w0, 0u, 0x4440u + a);       // byte a of the window, zero-extended
+    const uint32_t sel = 0x4321u + a * 0x1111u;            // the four bytes behind it ...
+    const uint32_t X0 = prmt(w0, w1, sel), X1 = prmt(w1, w2, sel);  // ... and the four after those
     uint4 lu;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(lu.x), "=r"(lu.y), "=r"(lu.z), "=r"(lu.w) : "r"(lut_s + ctrl * 16));
-    const uint32_t H0 = __byte_perm(X0, X1, lu.x) & lu.y, H1 = __byte_perm(X0, X1, lu.x >> 16) & lu.z;
+    const uint32_t H0 = prmt(X0, X1, lu.x) & lu.z, H1 = prmt(X0, X1, lu.y) & lu.w;
     // (low byte, high byte) pairs -> u16 fields, two per word
-    const uint32_t P01 = __byte_perm(fx.x, H0, 0x5140), P23 = __byte_perm(fx.x, H0, 0x7362);
-    const uint32_t P45 = __byte_perm(fx.y, H1, 0x5140), P67 = __byte_perm(fx.y, H1, 0x7362);
+    const uint32_t P01 = prmt(fx.x, H0, 0x5140), P23 = prmt(fx.x, H0, 0x7362);
+    const uint32_t P45 = prmt(fx.y, H1, 0x5140), P67 = prmt(fx.y, H1, 0x7362);
     // packed prefix sum: (a, b) * 0x10001 = (a, a + b); components stay below 2^16, so no carry crosses the halves
     c.x = P01 * 0x10001u;
     c.y = (P23 + (c.x >> 16)) * 0x10001u;
     c.z = (P45 + (c.y >> 16)) * 0x10001u;
     c.w = (P67 + (c.z >> 16)) * 0x10001u;
     // codes -> f16 subnormals (code * 2^-24), two per word
-    v.x = __byte_perm(fx.z, 0u, 0x4140);
-    v.y = __byte_perm(fx.z, 0u, 0x4342);
-    v.z = __byte_perm(fx.w, 0u, 0x4140);
-    v.w = __byte_perm(fx.w, 0u, 0x4342);
-    bytes += lu.w;
+    v.x = prmt(fx.z, 0u, 0x4140);
+    v.y = prmt(fx.z, 0u, 0x4342);
+    v.z = prmt(fx.w, 0u, 0x4140);
+    v.w = prmt(fx.w, 0u, 0x4342);
+    bytes += 1 + __popc(ctrl);
 }
 
 template <int D, class Q>
 __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream, const uint64_t (&post)[D],
                                               uint32_t lane8, uint32_t rounds, const Q& q, float (&acc)[D],
-                                              uint32_t& bytes, uint32_t lut_s, uint32_t pm0, uint32_t pm1) {
+                                              uint32_t& bytes, uint32_t lut_s) {
     const uint8_t* rec[D];
-    uint32_t nch[D];
+    uint32_t nch[D], eo[D];  // eo: offset of the lane's exception group in the coming round
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         rec[j] = stream + (post[j] >> 16) * RecVB::UNIT_BYTES;
         nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
         acc[j] = 0.f;
-        if (lane8 == 0) bytes += 16 * nch[j] + 16 * ((nch[j] + 7) >> 3);
+        eo[j] = lane8 < nch[j] ? __ldg(reinterpret_cast<const uint16_t*>(rec[j] + 16u * nch[j]) + lane8) : 0u;
+        if (lane8 == 0) bytes += 18 * nch[j];
     }
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t m = lane8 + 8 * r;
-        uint4 c[D], v[D];
+        uint4 c[D], v[D], fx[D];
+        uint32_t eo_next[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {  // every load of the round is issued before the first use
+            fx[j] = make_uint4(0, 0, 0, 0);
+            eo_next[j] = 0;
+            if (m < nch[j]) fx[j] = ld_stream(reinterpret_cast<const uint4*>(rec[j]) + m);
+            if (m + 8 < nch[j]) eo_next[j] = __ldg(reinterpret_cast<const uint16_t*>(rec[j] + 16u * nch[j]) + m + 8);
+        }
 #pragma unroll
         for (int j = 0; j < D; ++j) {  // a chunk past the end of a record is (0, +0.0) x 8: adds q * 0 = +-0
             c[j] = make_uint4(0, 0, 0, 0), v[j] = make_uint4(0, 0, 0, 0);
-            if (m < nch[j]) vb_decode(rec[j], nch[j], m, r, lane8, pm0, pm1, lut_s, c[j], v[j], bytes);
+            if (m < nch[j]) vb_decode(fx[j], rec[j] + 18u * nch[j] + eo[j], lut_s, c[j], v[j], bytes);
+            eo[j] = eo_next[j];
         }
         if constexpr (D == 2 && Q::HAS_DOT8) {
             q.dot2x(acc[0], acc[1], c, v);
@@ -840,65 +852,83 @@ struct RegHeap {
     }
 };
 
-// KHeap for any k (<= 1024): unsorted arrays in shared memory + tracked worst item.
+// KHeap for any k (<= 1024): the retained items sorted best-first in shared memory.  A call merges up to 32 candidates
+// (one per lane) in one step, like RegHeap::merge32: the result of pushing a set of items one by one is the k best of
+// (heap U set) whatever the order, so every item's final position is its rank in the union — a binary search of each
+// candidate in the sorted array, a count among the candidates, and an in-place shift of the retained items from the
+// worst chunk of 32 down to the best (an item only ever moves towards the worse end, by the number of candidates that
+// beat it, which grows with its position — so a chunk's writes never land on an unread item).
 struct SmemHeap {
     float* hs;
     uint32_t* hk;
-    uint32_t n, k, wkey, widx;
+    uint32_t n, k, wkey;
     float theta;
     __device__ __forceinline__ void reset(uint32_t kk, float* s, uint32_t* ky) {
-        hs = s, hk = ky, n = 0, k = kk, theta = 0.f, wkey = 0, widx = 0;
+        hs = s, hk = ky, n = 0, k = kk, theta = 0.f, wkey = 0;
     }
     __device__ __forceinline__ bool full() const { return n == k; }
-    __device__ __forceinline__ void find_worst(uint32_t lane) {
-        float s = 0.f;
-        uint32_t key = 0, idx = 0xffffffffu;
-        for (uint32_t i = lane; i < n; i += 32) {
-            const float si = hs[i];
-            const uint32_t ki = hk[i];
-            if (idx == 0xffffffffu || better(s, key, si, ki)) s = si, key = ki, idx = i;
+    // candidates of the lanes in `m`: keys distinct among themselves; each beats the current worst or the heap has room
+    __device__ __forceinline__ void merge(uint32_t m, const float sc, const uint32_t ky, uint32_t lane) {
+        bool c = (m >> lane) & 1u;
+        // retained items better than this lane's candidate = its lower bound in the sorted array (fixed trip count)
+        uint32_t hb = 0, len = n;
+        const uint32_t steps = 32 - __clz(n);
+        for (uint32_t st = 0; st < steps; ++st) {
+            const uint32_t half = len >> 1;
+            const bool right = len > 0 && better(hs[hb + half], hk[hb + half], sc, ky);
+            hb = right ? hb + half + 1 : hb;
+            len = right ? len - half - 1 : half;
         }
-        for (int sh = 16; sh > 0; sh >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, s, sh);
-            const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, sh);
-            const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, sh);
-            if (oi != 0xffffffffu && (idx == 0xffffffffu || better(s, key, os, ok))) s = os, key = ok, idx = oi;
+        if (c && hb < n && hk[hb] == ky) c = false;  // already retained (same document, same score, same position)
+        m = __ballot_sync(0xffffffffu, c);
+        if (!m) return;
+        uint32_t cb = 0;  // candidates better than this lane's candidate
+        for (uint32_t mm = m; mm; mm &= mm - 1) {
+            const int j = __ffs(mm) - 1;
+            cb += better(__shfl_sync(0xffffffffu, sc, j), __shfl_sync(0xffffffffu, ky, j), sc, ky);
         }
-        theta = s, wkey = key, widx = idx;
-    }
-    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane, bool = true) {
-        for (;;) {
-            const bool fl = n == k;
-            const bool c = have && (!fl || better(sc, ky, theta, wkey));
-            const uint32_t m = __ballot_sync(0xffffffffu, c);
-            if (!m) break;
-            const int src = __ffs(m) - 1;
-            const float bs = __shfl_sync(0xffffffffu, sc, src);
-            const uint32_t bk = __shfl_sync(0xffffffffu, ky, src);
-            if ((int)lane == src) have = false;
-            bool dup = false;
-            for (uint32_t hh = lane; hh < n; hh += 32) dup |= hk[hh] == bk;
-            if (__any_sync(0xffffffffu, dup)) continue;
-            const uint32_t slot = fl ? widx : n;
-            if (lane == 0) hs[slot] = bs, hk[slot] = bk;
-            if (!fl) ++n;
+        __syncwarp();
+        for (int base = n ? (int)((n - 1) & ~31u) : -32; base >= 0; base -= 32) {
+            const uint32_t i = (uint32_t)base + lane;
+            const bool valid = i < n;
+            const float si = valid ? hs[i] : 0.f;
+            const uint32_t ki = valid ? hk[i] : 0u;
+            uint32_t up = 0;  // candidates better than this retained item
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const int j = __ffs(mm) - 1;
+                up += better(__shfl_sync(0xffffffffu, sc, j), __shfl_sync(0xffffffffu, ky, j), si, ki);
+            }
             __syncwarp();
-            if (n == k) find_worst(lane);
+            if (valid && up && i + up < k) hs[i + up] = si, hk[i + up] = ki;
+            __syncwarp();
+        }
+        const uint32_t rc = hb + cb;
+        if (c && rc < k) hs[rc] = sc, hk[rc] = ky;
+        __syncwarp();
+        n = min(k, n + (uint32_t)__popc(m));
+        if (n == k) theta = hs[k - 1], wkey = hk[k - 1];
+    }
+    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t ky, uint32_t lane, bool distinct = true) {
+        const uint32_t m = __ballot_sync(0xffffffffu, have && (n < k || better(sc, ky, theta, wkey)));
+        if (!m) return;
+        if (distinct) {
+            merge(m, sc, ky, lane);
+        } else {  // keys may repeat inside the call (kNN refine): one candidate at a time, re-filtered by the live heap
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const uint32_t one = mm & (0u - mm);
+                const uint32_t ok = __ballot_sync(0xffffffffu, (one >> lane) & 1u && (n < k || better(sc, ky, theta, wkey)));
+                if (ok) merge(ok, sc, ky, lane);
+            }
         }
     }
     __device__ __forceinline__ void store_keys(uint32_t* dst, uint32_t lane) const {
         for (uint32_t i = lane; i < n; i += 32) dst[i] = hk[i];
     }
     __device__ __forceinline__ void write_sorted(uint32_t lane, uint32_t* out_keys, float* out_scores) const {
-        for (uint32_t i = lane; i < n; i += 32) {
-            const float si = hs[i];
-            const uint32_t ki = hk[i];
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < n; ++j) rank += better(hs[j], hk[j], si, ki);
-            out_keys[rank] = ki;
-            out_scores[rank] = si;
+        for (uint32_t i = lane; i < k; i += 32) {
+            out_keys[i] = i < n ? hk[i] : 0xffffffffu;
+            out_scores[i] = i < n ? hs[i] : -INFINITY;
         }
-        for (uint32_t i = n + lane; i < k; i += 32) out_keys[i] = 0xffffffffu, out_scores[i] = -INFINITY;
     }
 };
 
@@ -942,13 +972,10 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     const uint32_t lane8 = tid & 7, grp = tid >> 3;
     const uint32_t k = a.k;
 
-    // DotVByte: control bytes of the round's chunks BEFORE this lane's (words 0 / 1 of the round header)
-    const uint32_t vb_pm0 = lane8 >= 4 ? 0xffffffffu : (1u << (8 * lane8)) - 1u;
-    const uint32_t vb_pm1 = lane8 <= 4 ? 0u : (1u << (8 * (lane8 - 4))) - 1u;
     // bytes of a posting's record (DotVByte: without the exception area's exact size, ~4 per chunk)
     auto rec_bytes = [&](uint64_t pst) -> uint32_t {
         const uint32_t nch = ((uint32_t)(pst & 0xffffu) + 7) >> 3;
-        if constexpr (is_vbyte<R>::value) return 20 * nch + 16 * ((nch + 7) >> 3);
+        if constexpr (is_vbyte<R>::value) return 23 * nch;
         else return nch * R::CHUNK_BYTES;
     };
     H heap;  // live in warp 0 only
@@ -1016,7 +1043,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             float acc[D];
             if constexpr (is_vbyte<R>::value)
                 score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, acc, st_units,
-                                 (uint32_t)__cvta_generic_to_shared(s_vb_lut), vb_pm0, vb_pm1);
+                                 (uint32_t)__cvta_generic_to_shared(s_vb_lut));
             else
                 score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, a.value_scale, acc);
 #pragma unroll

@@ -79,7 +79,7 @@ struct SgpuIndex {
     cudaStream_t own_stream = nullptr;  // the library's private stream
     cudaEvent_t ev[8] = {};
     // image
-    DevBuf lists, postings, blk_post_off, blk_min, blk_quant, sc_comp, sc_run_off, ent_blk, ent_code, fwd, rec_start, knn_posts;
+    DevBuf lists, postings, blk_post_off, blk_min, blk_quant, sc_comp, sc_run_off, sc_skip, ent_blk, ent_code, fwd, rec_start, knn_posts;
     sgpu::DevIndex ix{};
     uint64_t image_bytes = 0;
     uint32_t max_blocks = 0;      // largest number of blocks of any list
@@ -279,6 +279,7 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
                    TE = v->list_ent_start[dim];
     std::vector<ListHdr> hdr(dim);
     uint32_t max_blocks = 0, max_block_docs = 0;
+    uint64_t n_skip_total = 0;
     for (uint64_t l = 0; l < dim; ++l) {
         ListHdr& h = hdr[l];
         h.post_base = v->list_post_start[l];
@@ -288,7 +289,12 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
         h.n_blk = (uint32_t)(v->list_blk_start[l + 1] - v->list_blk_start[l]);
         h.n_sc = (uint32_t)(v->list_sc_start[l + 1] - v->list_sc_start[l]);
         h.n_post = (uint32_t)(v->list_post_start[l + 1] - v->list_post_start[l]);
-        h.pad = 0;
+        h.skip_base = (uint32_t)n_skip_total;
+        n_skip_total += (h.n_sc + 31) >> 5;
+        if (n_skip_total >= (1ull << 32)) {
+            shost::set_error("summary component directory larger than 2^32 entries");
+            return SGPU_EUNSUPPORTED;
+        }
         if (h.n_blk > 65535) {
             shost::set_error("list with more than 65535 blocks");
             return SGPU_EINVAL;
@@ -312,6 +318,11 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     if (int rc = upload(ix->blk_quant, v->blk_quant, TB, st, &total)) return rc;
     if (int rc = upload(ix->sc_comp, v->sc_comp, TSC, st, &total)) return rc;
     if (int rc = upload(ix->sc_run_off, v->sc_run_off, TSC + dim, st, &total)) return rc;
+    CK(ix->sc_skip.ensure(std::max<uint64_t>(n_skip_total, 1) * 4));
+    total += n_skip_total * 4;
+    k_build_skip<<<(unsigned)((dim + 7) / 8), 256, 0, st>>>(ix->lists.as<ListHdr>(), (uint32_t)dim, ix->sc_comp.as<uint32_t>(),
+                                                           ix->sc_skip.as<uint32_t>());
+    CK(cudaGetLastError());
     if (int rc = upload(ix->ent_blk, v->ent_blk, TE, st, &total)) return rc;
     if (int rc = upload(ix->ent_code, v->ent_code, TE, st, &total)) return rc;
     CK(cudaStreamSynchronize(st));
@@ -324,6 +335,7 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     d.blk_quant = ix->blk_quant.as<float>();
     d.sc_comp = ix->sc_comp.as<uint32_t>();
     d.sc_run_off = ix->sc_run_off.as<uint32_t>();
+    d.sc_skip = ix->sc_skip.as<uint32_t>();
     d.ent_blk = ix->ent_blk.as<uint16_t>();
     d.ent_code = ix->ent_code.as<uint8_t>();
     d.fwd = ix->fwd.as<uint4>();
@@ -612,7 +624,7 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         pd.launches += 2;
         CK(cudaEventRecord(ix->ev[3], st));
         const uint64_t tasks = (uint64_t)n * cut_eff;
-        k_est<<<(unsigned)tasks, EST_THREADS, 0, st>>>(ix->ix, b, sc);
+        k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);
         CK(cudaGetLastError());
         ++pd.launches;
         if (ad.first_sorted) {
@@ -965,6 +977,251 @@ int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64
     return SGPU_OK;
 }
 
-const char* sgpu_version(void) { return "seismic_b200 0.1.0 sm_100a"; }
+const char* sgpu_version(void) { return "seismic_b200 0.2.0 sm_100a"; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU group: replicas + one NCCL gather (see include/seismic_b200.h)
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+#include <dlfcn.h>
+
+namespace {
+
+// the handful of NCCL entry points the gather needs, resolved from libnccl.so.2 at run time (if the process already
+// holds an NCCL with that soname — e.g. torch's — dlopen returns it)
+typedef struct ncclComm* nccl_comm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+        Send = (decltype(Send))dlsym(lib, "ncclSend");
+        Recv = (decltype(Recv))dlsym(lib, "ncclRecv");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Send && Recv && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclUint8 = 1;  // ncclUint8 (nccl.h)
+
+#define NK(expr)                                                                                         \
+    do {                                                                                                 \
+        int _r = (expr);                                                                                 \
+        if (_r != 0) {                                                                                   \
+            shost::set_error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));                     \
+            return SGPU_ECUDA;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+}  // namespace
+
+struct SgpuGroup {
+    std::vector<SgpuIndex*> idx;     // one replica per device
+    std::vector<nccl_comm_t> comms;  // one communicator per device (ncclCommInitAll)
+    std::vector<Pending> pend;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+    ~SgpuGroup() {
+        for (auto c : comms)
+            if (c) g_nccl.CommDestroy(c);
+        for (auto* i : idx) delete i;
+        if (ev_g0) cudaEventDestroy(ev_g0);
+        if (ev_g1) cudaEventDestroy(ev_g1);
+    }
+};
+
+namespace {
+
+int group_create_impl(const SgpuIndexView* view, const int* devices, int n, SgpuGroup** out) {
+    if (!view || !devices || !out || n <= 0) {
+        shost::set_error("sgpu_group_create: bad argument");
+        return SGPU_EINVAL;
+    }
+    for (int a = 0; a < n; ++a)
+        for (int b2 = a + 1; b2 < n; ++b2)
+            if (devices[a] == devices[b2]) {
+                shost::set_error("sgpu_group_create: duplicate device");
+                return SGPU_EINVAL;
+            }
+    std::unique_ptr<SgpuGroup> g(new SgpuGroup());
+    for (int r = 0; r < n; ++r) {
+        SgpuIndex* ix = nullptr;
+        if (int rc = create_impl(view, devices[r], &ix)) return rc;
+        g->idx.push_back(ix);
+    }
+    g->pend.resize(n);
+    if (n > 1) {
+        if (!g_nccl.load()) {
+            shost::set_error("sgpu_group_create: libnccl.so.2 not found (needed for the multi-GPU gather)");
+            return SGPU_ECUDA;
+        }
+        g->comms.assign(n, nullptr);
+        NK(g_nccl.CommInitAll(g->comms.data(), n, devices));
+    }
+    CK(cudaSetDevice(devices[0]));
+    CK(cudaEventCreate(&g->ev_g0));
+    CK(cudaEventCreate(&g->ev_g1));
+    *out = g.release();
+    return SGPU_OK;
+}
+
+// contiguous, balanced ranges: the first nq % n devices get one extra query
+inline void shard_bounds(uint64_t nq, int r, int n, uint64_t* lo, uint64_t* hi) {
+    const uint64_t base = nq / n, extra = nq % n;
+    *lo = r * base + std::min<uint64_t>(r, extra);
+    *hi = *lo + base + ((uint64_t)r < extra ? 1 : 0);
+}
+
+int group_search_impl(SgpuGroup* g, const SgpuQueryBatch* q, const SgpuSearchParams* p, uint64_t* out_ids,
+                      float* out_scores, uint32_t* out_counts, SgpuSearchStats* stats, float* ms_gather) {
+    if (!g || !q || !p || !out_ids || !out_scores || !out_counts) {
+        shost::set_error("sgpu_group_batch_search: null argument");
+        return SGPU_EINVAL;
+    }
+    if (p->k == 0) {
+        shost::set_error("k must be > 0 (KHeap::new asserts k > 0)");
+        return SGPU_EINVAL;
+    }
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (ms_gather) *ms_gather = 0.f;
+    const int n = (int)g->idx.size();
+    const uint64_t nq = q->n_queries, k = p->k;
+    if (nq == 0) return SGPU_OK;
+    SgpuIndex* root = g->idx[0];
+    // device 0 holds the gathered tuples of the whole batch
+    CK(cudaSetDevice(root->device));
+    CK(root->d_out_ids.ensure(nq * k * 8));
+    CK(root->d_out_scores.ensure(nq * k * 4));
+    CK(root->d_out_counts.ensure(nq * 4));
+    // ---- every device: stage its slice, copy in, enqueue the search (nothing here waits for a device)
+    for (int r = 0; r < n; ++r) {
+        SgpuIndex* ix = g->idx[r];
+        uint64_t lo, hi;
+        shard_bounds(nq, r, n, &lo, &hi);
+        g->pend[r] = Pending{};
+        if (hi == lo) continue;
+        CK(cudaSetDevice(ix->device));
+        cudaStream_t st = ix->stream;
+        const uint64_t nr = hi - lo, e0 = q->offsets[lo], nnz = q->offsets[hi] - e0;
+        const size_t b_off = (nr + 1) * 8, b_c = nnz * 4;
+        CK(ix->h_in.ensure(b_off + 2 * b_c));
+        uint8_t* hin = ix->h_in.as<uint8_t>();
+        uint64_t* ho = reinterpret_cast<uint64_t*>(hin);
+        for (uint64_t i = 0; i <= nr; ++i) ho[i] = q->offsets[lo + i] - e0;
+        if (nnz) {
+            std::memcpy(hin + b_off, q->comps + e0, b_c);
+            std::memcpy(hin + b_off + b_c, q->values + e0, b_c);
+        }
+        CK(ix->d_qoff.ensure(b_off));
+        CK(ix->d_qcomps.ensure(std::max<size_t>(b_c, 4)));
+        CK(ix->d_qvals.ensure(std::max<size_t>(b_c, 4)));
+        CK(cudaMemcpyAsync(ix->d_qoff.p, hin, b_off, cudaMemcpyHostToDevice, st));
+        if (nnz) {
+            CK(cudaMemcpyAsync(ix->d_qcomps.p, hin + b_off, b_c, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ix->d_qvals.p, hin + b_off + b_c, b_c, cudaMemcpyHostToDevice, st));
+        }
+        SgpuQueryBatch dq{nr, ix->d_qoff.as<uint64_t>(), ix->d_qcomps.as<uint32_t>(), ix->d_qvals.as<float>()};
+        uint64_t* d_ids;
+        float* d_sc;
+        uint32_t* d_cnt;
+        if (r == 0) {  // device 0 writes its share straight into the gathered buffers
+            d_ids = root->d_out_ids.as<uint64_t>() + lo * k;
+            d_sc = root->d_out_scores.as<float>() + lo * k;
+            d_cnt = root->d_out_counts.as<uint32_t>() + lo;
+        } else {
+            CK(ix->d_out_ids.ensure(nr * k * 8));
+            CK(ix->d_out_scores.ensure(nr * k * 4));
+            CK(ix->d_out_counts.ensure(nr * 4));
+            d_ids = ix->d_out_ids.as<uint64_t>(), d_sc = ix->d_out_scores.as<float>(), d_cnt = ix->d_out_counts.as<uint32_t>();
+        }
+        if (int rc = enqueue_search(ix, &dq, p, d_ids, d_sc, d_cnt, g->pend[r])) return rc;
+    }
+    // ---- validation / long-query passes of every device (one synchronisation each), then ONE fused gather
+    for (int r = 0; r < n; ++r) {
+        CK(cudaSetDevice(g->idx[r]->device));
+        if (int rc = finish_search(g->idx[r], g->pend[r], r == 0 ? stats : nullptr, nullptr)) return rc;
+    }
+    CK(cudaSetDevice(root->device));
+    CK(cudaEventRecord(g->ev_g0, root->stream));
+    if (n > 1) {
+        NK(g_nccl.GroupStart());
+        for (int r = 1; r < n; ++r) {
+            uint64_t lo, hi;
+            shard_bounds(nq, r, n, &lo, &hi);
+            const uint64_t nr = hi - lo;
+            if (!nr) continue;
+            SgpuIndex* ix = g->idx[r];
+            NK(g_nccl.Send(ix->d_out_ids.p, nr * k * 8, kNcclUint8, 0, g->comms[r], ix->stream));
+            NK(g_nccl.Send(ix->d_out_scores.p, nr * k * 4, kNcclUint8, 0, g->comms[r], ix->stream));
+            NK(g_nccl.Send(ix->d_out_counts.p, nr * 4, kNcclUint8, 0, g->comms[r], ix->stream));
+            NK(g_nccl.Recv(root->d_out_ids.as<uint64_t>() + lo * k, nr * k * 8, kNcclUint8, r, g->comms[0], root->stream));
+            NK(g_nccl.Recv(root->d_out_scores.as<float>() + lo * k, nr * k * 4, kNcclUint8, r, g->comms[0], root->stream));
+            NK(g_nccl.Recv(root->d_out_counts.as<uint32_t>() + lo, nr * 4, kNcclUint8, r, g->comms[0], root->stream));
+        }
+        NK(g_nccl.GroupEnd());
+    }
+    CK(cudaSetDevice(root->device));
+    CK(cudaEventRecord(g->ev_g1, root->stream));
+    const size_t o_ids = nq * k * 8, o_sc = nq * k * 4, o_cnt = nq * 4;
+    CK(root->h_out.ensure(o_ids + o_sc + o_cnt));
+    uint8_t* hout = root->h_out.as<uint8_t>();
+    CK(cudaMemcpyAsync(hout, root->d_out_ids.p, o_ids, cudaMemcpyDeviceToHost, root->stream));
+    CK(cudaMemcpyAsync(hout + o_ids, root->d_out_scores.p, o_sc, cudaMemcpyDeviceToHost, root->stream));
+    CK(cudaMemcpyAsync(hout + o_ids + o_sc, root->d_out_counts.p, o_cnt, cudaMemcpyDeviceToHost, root->stream));
+    CK(cudaStreamSynchronize(root->stream));
+    for (int r = 1; r < n; ++r) {  // the senders' streams are done once the receiver is; keep the handles quiescent
+        CK(cudaSetDevice(g->idx[r]->device));
+        CK(cudaStreamSynchronize(g->idx[r]->stream));
+    }
+    if (ms_gather) {
+        CK(cudaSetDevice(root->device));
+        CK(cudaEventElapsedTime(ms_gather, g->ev_g0, g->ev_g1));
+    }
+    std::memcpy(out_ids, hout, o_ids);
+    std::memcpy(out_scores, hout + o_ids, o_sc);
+    std::memcpy(out_counts, hout + o_ids + o_sc, o_cnt);
+    return SGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgpu_group_create(const SgpuIndexView* view, const int* devices, int n_devices, SgpuGroup** out) {
+    try {
+        return group_create_impl(view, devices, n_devices, out);
+    } catch (const std::bad_alloc&) {
+        shost::set_error("out of host memory");
+        return SGPU_ENOMEM;
+    }
+}
+void sgpu_group_destroy(SgpuGroup* group) { delete group; }
+int sgpu_group_size(const SgpuGroup* group) { return group ? (int)group->idx.size() : 0; }
+int sgpu_group_set_knn(SgpuGroup* group, const uint64_t* neighbours, uint32_t knn_dim) {
+    if (!group) return SGPU_EINVAL;
+    for (auto* ix : group->idx)
+        if (int rc = set_knn_impl(ix, neighbours, knn_dim)) return rc;
+    return SGPU_OK;
+}
+int sgpu_group_batch_search(SgpuGroup* group, const SgpuQueryBatch* queries, const SgpuSearchParams* params,
+                            uint64_t* out_ids, float* out_scores, uint32_t* out_counts, SgpuSearchStats* stats,
+                            float* ms_gather) {
+    return group_search_impl(group, queries, params, out_ids, out_scores, out_counts, stats, ms_gather);
+}
 
 }  // extern "C"

@@ -14,7 +14,7 @@ struct ListHdr {
     uint32_t n_blk;
     uint32_t n_sc;
     uint32_t n_post;
-    uint32_t pad;
+    uint32_t skip_base;  // into sc_skip: ceil(n_sc / 32) entries, the LAST summary component of every group of 32
 };
 
 struct DevIndex {
@@ -25,6 +25,7 @@ struct DevIndex {
     const float* blk_quant;
     const uint32_t* sc_comp;
     const uint32_t* sc_run_off;
+    const uint32_t* sc_skip;    // per list: last component id of every 32 summary components (directory of sc_comp)
     const uint16_t* ent_blk;
     const uint8_t* ent_code;
     const uint4* fwd;           // record buffer, 2 x uint4 per chunk

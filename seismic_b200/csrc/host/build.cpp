@@ -727,18 +727,18 @@ void fill_view(const ShostIndex& idx, SgpuIndexView* v) {
 // GPU lane decodes one chunk of 8 components with wide aligned loads and byte permutes.
 //
 //   value    u8 code, value = code * scale, scale = (largest f16 value of the collection) / 255   (FixedU8)
-//   record   16-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)), chunks in rounds of 8 (nr = ceil(nch/8)):
+//   record   16-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)):
 //     fixed  16 bytes per chunk: lo[8] = LOW bytes of (first component, gap 1, ..., gap 7), then val[8] = the 8 codes
 //            (tail of the last chunk: gap 0, code 0)
-//     round  16 bytes per round: ctrl[8] = control byte of each of the round's chunks, exc_off u32 = offset of the
-//            round's first exception byte inside the record's exception area, u32 0
-//            control byte: bit 7 = the first component has a HIGH byte, bit j-1 = gap j has one (j = 1..7)
-//     exc    the high bytes that exist, chunk after chunk: first component, then gaps 1..7
+//     cum    u16 per chunk: offset of the chunk's exception group inside the record's exception area
+//     exc    one group per chunk: the control byte (bit 7 = the first component has a HIGH byte, bit j-1 = gap j has
+//            one, j = 1..7), then the high bytes that exist — first component, then gaps 1..7
 //     zero padding to a multiple of 16 bytes
 //   fwd_offsets[i]  byte offset of record i;  fwd_nnz[i] number of components;  postings = (offset/16 << 16) | nnz
-// A chunk is self-contained given its round header (absolute first component; exception offset = exc_off +
-// popcount of the preceding control bytes of the round), so the 8 lanes of a GPU group decode the 8 chunks of a round
-// in parallel.
+// Every chunk is self-contained given its u16 offset (absolute first component), so the 8 lanes of a GPU group decode
+// 8 chunks in parallel, and the loads of a chunk (its 16 fixed bytes, its exception group) do not depend on any
+// other chunk's data.  (A record has at most 8192 chunks, hence at most 2 * 8192 + 255 exception-area bytes — the
+// gaps of one vector sum to less than 2^16, so at most 255 of them need a high byte: the offsets fit u16.)
 namespace shost {
 
 int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
@@ -765,8 +765,8 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t d = b; d < e; ++d) {
             const uint64_t s = off[d], n = off[d + 1] - s;
-            const uint32_t nch = (uint32_t)((n + 7) >> 3), nr = (nch + 7) >> 3;
-            uint64_t bytes = 16ull * nch + 16ull * nr;
+            const uint32_t nch = (uint32_t)((n + 7) >> 3);
+            uint64_t bytes = 16ull * nch + 2ull * nch + nch;  // fixed parts, offsets, control bytes
             for (uint32_t m = 0; m < nch; ++m)
                 for (uint32_t f = 0; f < 8; ++f) bytes += field(s, n, m, f) >= 256 ? 1 : 0;
             boff[d + 1] = (bytes + 15) & ~15ull;
@@ -789,19 +789,18 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t d = b; d < e; ++d) {
             const uint64_t s = off[d], n = off[d + 1] - s;
-            const uint32_t nch = (uint32_t)((n + 7) >> 3), nr = (nch + 7) >> 3;
+            const uint32_t nch = (uint32_t)((n + 7) >> 3);
             nnzs[d] = (uint16_t)n;
             uint8_t* rec = stream + boff[d];
             std::memset(rec, 0, boff[d + 1] - boff[d]);
-            uint8_t* rounds = rec + 16ull * nch;
-            uint8_t* exc0 = rounds + 16ull * nr;
+            uint8_t* cum = rec + 16ull * nch;
+            uint8_t* exc0 = cum + 2ull * nch;
             uint8_t* exc = exc0;
             for (uint32_t m = 0; m < nch; ++m) {
-                if ((m & 7) == 0) {
-                    const uint32_t eo = (uint32_t)(exc - exc0);
-                    std::memcpy(rounds + 16ull * (m >> 3) + 8, &eo, 4);
-                }
+                const uint16_t eo = (uint16_t)(exc - exc0);
+                std::memcpy(cum + 2ull * m, &eo, 2);
                 uint8_t* fx = rec + 16ull * m;
+                uint8_t* ctrl = exc++;
                 uint8_t c = 0;
                 for (uint32_t f = 0; f < 8; ++f) {
                     const uint64_t i = (uint64_t)m * 8 + f;
@@ -814,7 +813,7 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
                         c |= (uint8_t)(f == 0 ? 0x80u : (1u << (f - 1)));
                     }
                 }
-                rounds[16ull * (m >> 3) + (m & 7)] = c;
+                *ctrl = c;
             }
         }
     });

@@ -145,10 +145,9 @@ class PyIndex:
 def decode_dotvbyte(host):
     """Independent decoder of the DotVByte forward index (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte;
     the reference's own byte format lives in vectorium).  Per document, 16-byte aligned: [16 bytes per chunk of 8
-    components: 8 low bytes of (first component, gap 1..7) | 8 u8 codes][16 bytes per round of 8 chunks: 8 control
-    bytes | u32 offset of the round's first exception byte | u32 0][exception area: the high bytes that exist, in
-    order].  Control byte: bit 7 = first component has a high byte, bit j-1 = gap j has one.
-    Returns CSR (offsets, components, values = code * scale, codes)."""
+    components: 8 low bytes of (first component, gap 1..7) | 8 u8 codes][u16 per chunk: offset of its exception group]
+    [exception groups: control byte, then the high bytes that exist, in order].  Control byte: bit 7 = first component
+    has a high byte, bit j-1 = gap j has one.  Returns CSR (offsets, components, values = code * scale, codes)."""
     from seismic_b200 import _native as N
     v = host.view
     n = host.len
@@ -162,15 +161,14 @@ def decode_dotvbyte(host):
         rec = stream[int(fo[d]):int(fo[d + 1])]
         ln = int(nnzs[d])
         nch = (ln + 7) // 8
-        nr = (nch + 7) // 8
-        rounds = rec[16 * nch: 16 * (nch + nr)]
-        exc = rec[16 * (nch + nr):]
-        e = 0
+        cum = rec[16 * nch: 18 * nch].view(np.uint16)
+        exc = rec[18 * nch:]
+        running = 0
         for m in range(nch):
             fx = rec[16 * m: 16 * m + 16]
-            ctrl = int(rounds[16 * (m // 8) + (m % 8)])
-            if m % 8 == 0:
-                assert int(rounds[16 * (m // 8) + 8: 16 * (m // 8) + 12].view(np.uint32)[0]) == e
+            e = int(cum[m])
+            assert e == running, "exception groups are laid end to end"
+            ctrl = int(exc[e]); e += 1
             c = 0
             for f in range(8):
                 field = int(fx[f])
@@ -184,5 +182,7 @@ def decode_dotvbyte(host):
                     vals.append(np.float32(np.float32(fx[8 + f]) * scale))
                 else:
                     assert field == 0 and fx[8 + f] == 0
+            running = e
+        assert not rec[18 * nch + running:].any(), "padding must be zero"
         off.append(len(comps))
     return np.array(off, np.uint64), np.array(comps, np.uint32), np.array(vals, np.float32), np.array(codes, np.uint8)

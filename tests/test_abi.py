@@ -70,4 +70,20 @@ def test_product_never_imports_oracle():
         elif p.suffix in {".cpp", ".hpp", ".cu", ".cuh", ".h"}:
             text = p.read_text()
             assert not re.search(r"#\s*include[^\n]*oracle", text), p
-            assert "liboracle" not in text and "dlopen" not in text, p
+            assert "liboracle" not in text, p
+            if "dlopen" in text:  # the only run-time loaded library is NCCL (multi-GPU gather, sgpu_group_*)
+                assert p.name == "sgpu_api.cu" and re.findall(r'"(lib[^"]*\.so[^"]*)"', text) == ["libnccl.so.2", "libnccl.so"], p
+
+
+def test_group_entry_fails_loudly_without_gpu(native, synth_small):
+    """sgpu_group_create: bad arguments are rejected; without a CUDA device it raises (no CPU fallback)."""
+    import torch
+    from seismic_b200 import GpuGroup
+    _, _, index = synth_small
+    with pytest.raises(ValueError):
+        GpuGroup(index, [])
+    with pytest.raises(ValueError):
+        GpuGroup(index, [0, 0])
+    if not torch.cuda.is_available():
+        with pytest.raises(native.SeismicError):
+            GpuGroup(index, [0])

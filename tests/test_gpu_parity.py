@@ -352,3 +352,26 @@ def test_exact_search_other_layouts(oracle_mod, comp_bits, value_kind, dim):
     ref = oracle_mod.exact_search(index.view, q.offsets, q.comps, q.values, 10)
     got = g.exact_search(q.offsets, q.comps, q.values, 10)
     assert_same(got, ref, f"exact comp_bits={comp_bits} value_kind={value_kind}")
+
+
+def test_group_entry_single_and_multi_device(oracle_mod, synth_pruned):
+    """sgpu_group_batch_search: the batch split over the devices of the box + one NCCL gather returns exactly the
+    single-device (= oracle) results, in input order.  Runs on however many GPUs are visible (1 GPU: the split and the
+    gather degenerate, the entry point is still exercised)."""
+    import torch
+    from seismic_b200 import GpuGroup
+    _, q, index = synth_pruned
+    n_dev = min(torch.cuda.device_count(), 8)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 3, 0.8)
+    for devs in ([0], list(range(n_dev))):
+        g = GpuGroup(index, devs)
+        assert len(g) == len(devs)
+        got = g.batch_search(q.offsets, q.comps, q.values, 10, 3, 0.8)
+        assert_same(got, ref, f"group over {devs}")
+        # a batch smaller than the group: some devices get nothing
+        small = (q.offsets[:2].copy(), q.comps[: int(q.offsets[1])], q.values[: int(q.offsets[1])])
+        got1 = g.batch_search(*small, 10, 3, 0.8)
+        assert (got1[0][0] == ref[0][0]).all()
+        with pytest.raises(ValueError):
+            g.batch_search(np.array([0, 2], np.uint64), np.array([9, 3], np.uint32), np.ones(2, np.float32), 10, 3, 0.8)
+        del g
