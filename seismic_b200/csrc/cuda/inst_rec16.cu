@@ -10,6 +10,10 @@ kern_t pick_rec16(QueryKind q, bool small_k) {
         default: return nullptr;
     }
 }
+kern_t pick_rec16_tma(bool small_k) {  // byte-index query, records staged by TMA; 3 CTAs / SM
+    return small_k ? (kern_t)k_search<256, 3, 2, ByteQuery, RegHeap, Rec16, true>
+                   : (kern_t)k_search<256, 3, 2, ByteQuery, SmemHeap, Rec16, true>;
+}
 exact_t pick_exact_rec16(bool dense) {
     return dense ? (exact_t)k_exact_partial<DenseQuery, Rec16> : (exact_t)k_exact_partial<SortedQuery, Rec16>;
 }

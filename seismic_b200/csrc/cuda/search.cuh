@@ -40,9 +40,6 @@ constexpr int HQ_SLOTS = 1 << HQ_LOG2_SLOTS;
 constexpr int HQ_MAX_NNZ = 128;  // HashQuery: queries with more components take the dense kernel
 constexpr int HQ_TRIES = 64;
 constexpr int DENSE_THREADS = 1024;
-#ifndef SGPU_LD256
-#define SGPU_LD256 0
-#endif
 #ifndef SGPU_VB_PRMT
 #define SGPU_VB_PRMT 1  // DotVByte: byte-permute decode of the gaps (0: sequential 64-bit shifts)
 #endif
@@ -77,26 +74,59 @@ struct SearchArgs {
     uint32_t* out_counts;      // [nq]
 };
 
+#ifndef SGPU_LD_MODE
+#define SGPU_LD_MODE 2  // A/B builds (same box, 1 M docs, ms per 10 k queries): 0 = ld.global.nc.L1::no_allocate 4.99,
+                        // 1 = ld.global.cg (L2 only) 4.98, 2 = ld.global.nc (default L1 policy) 4.92
+#endif
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     uint4 r;
+#if SGPU_LD_MODE == 1
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+#elif SGPU_LD_MODE == 2
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+#endif
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
 }
-// one whole 32-byte chunk (8 components + 8 values): a single 256-bit load (LDG.E.256, sm_100) or two 128-bit loads
-__device__ __forceinline__ void ld_chunk(const uint4* p, uint4& c, uint4& v) {
-#if SGPU_LD256
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
-#else
-    c = ld_stream(p);
-    v = ld_stream(p + 1);
-#endif
+// One 32-byte chunk of the u16 / f16 layout (8 components + 8 values) with two 128-bit loads.  Chunks 4..7 of every
+// round of 8 are stored [values | components] instead of [components | values] (`sw` = bit 2 of the chunk index): when
+// the 8 lanes of a group read the same half of their chunks from SHARED memory (TMA-staged rounds) the 16-byte pieces
+// then fall into 8 distinct bank quads; from global memory the order is irrelevant.
+__device__ __forceinline__ void ld_chunk(const uint4* p, uint32_t sw, uint4& c, uint4& v) {
+    c = ld_stream(p + sw);
+    v = ld_stream(p + (sw ^ 1u));
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- TMA (bulk async copy, 1-D) + mbarrier: the staging ring of the TMA variant of k_search ----------------------
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {  // one arrival + `bytes` expected
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nMBW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MBD;\nbra MBW;\nMBD:\n}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+constexpr int TMA_ROUND_BYTES = 256;                  // one round of one document: 8 chunks of 32 bytes
+constexpr int TMA_WARP_BYTES = 8 * TMA_ROUND_BYTES;   // per warp: one round of its 4 x 2 documents
 __device__ __forceinline__ float h_lo(uint32_t vw) { return __low2float(*reinterpret_cast<const __half2*>(&vw)); }
 __device__ __forceinline__ float h_hi(uint32_t vw) { return __high2float(*reinterpret_cast<const __half2*>(&vw)); }
 
@@ -417,8 +447,8 @@ struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x 
     static constexpr int CHUNK_BYTES = 32;
     static constexpr int UNIT_BYTES = 32;  // unit of the posting's start field
     struct Chunk { uint4 c, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
-        ld_chunk(reinterpret_cast<const uint4*>(p), k.c, k.v);
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t m) {
+        ld_chunk(reinterpret_cast<const uint4*>(p), (m >> 2) & 1u, k.c, k.v);
     }
     template <class Q>
     static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float) {
@@ -437,7 +467,7 @@ struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16
     static constexpr int CHUNK_BYTES = 48;
     static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c0, c1, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         const uint4* p4 = reinterpret_cast<const uint4*>(p);
         k.c0 = ld_stream(p4);
         k.c1 = ld_stream(p4 + 1);
@@ -469,8 +499,8 @@ struct Rec16V2 {
     static constexpr int CHUNK_BYTES = 32;
     static constexpr int UNIT_BYTES = 32;
     struct Chunk { uint4 c, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
-        ld_chunk(reinterpret_cast<const uint4*>(p), k.c, k.v);
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
+        ld_chunk(reinterpret_cast<const uint4*>(p), 0u, k.c, k.v);
     }
     static __device__ __forceinline__ float val(uint32_t vw, bool hi, float scale) {
         if constexpr (KIND == 1) return __uint_as_float(hi ? (vw & 0xffff0000u) : (vw << 16));
@@ -492,7 +522,7 @@ struct Rec16F32 {  // chunk = [8 x u16 | 8 x f32] = 48 bytes, unit 16 bytes
     static constexpr int CHUNK_BYTES = 48;
     static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c, v0, v1; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         const uint4* p4 = reinterpret_cast<const uint4*>(p);
         k.c = ld_stream(p4);
         k.v0 = ld_stream(p4 + 1);
@@ -515,7 +545,7 @@ struct Rec16U8 {  // chunk = [8 x u16 | 8 x u8] = 24 bytes, unit 8 bytes (8-byte
     static constexpr int CHUNK_BYTES = 24;
     static constexpr int UNIT_BYTES = 8;
     struct Chunk { uint2 c0, c1, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         const uint2* p2 = reinterpret_cast<const uint2*>(p);
         k.c0 = __ldg(p2);
         k.c1 = __ldg(p2 + 1);
@@ -544,7 +574,7 @@ struct Rec32V {
     static constexpr int UNIT_BYTES = CHUNK_BYTES % 32 == 0 ? 32 : (CHUNK_BYTES % 16 == 0 ? 16 : 8);
     static constexpr int WORDS = CHUNK_BYTES / 4;
     struct Chunk { uint32_t w[WORDS]; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         if constexpr (CHUNK_BYTES % 16 == 0) {
             const uint4* p4 = reinterpret_cast<const uint4*>(p);
 #pragma unroll
@@ -586,7 +616,7 @@ __device__ __forceinline__ float score_rec(const char* __restrict__ rec, uint32_
     float acc = 0.f;
     for (uint32_t m = lane8; m < nch; m += 8) {
         typename R::Chunk k;
-        R::load(rec + (size_t)R::CHUNK_BYTES * m, k);
+        R::load(rec + (size_t)R::CHUNK_BYTES * m, k, m);
         acc = R::dot(acc, k, q, scale);
     }
     return acc;
@@ -618,14 +648,14 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 c[j] = make_uint4(0, 0, 0, 0), v[j] = make_uint4(0, 0, 0, 0);
-                if (m < nch[j]) ld_chunk(reinterpret_cast<const uint4*>(rec[j] + (size_t)256 * r), c[j], v[j]);
+                if (m < nch[j]) ld_chunk(reinterpret_cast<const uint4*>(rec[j] + (size_t)256 * r), (lane8 >> 2) & 1u, c[j], v[j]);
             }
             q.dot2x(acc[0], acc[1], c, v);
         } else {
             typename R::Chunk k[D];
 #pragma unroll
             for (int j = 0; j < D; ++j)
-                if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j]);
+                if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j], m);
 #pragma unroll
             for (int j = 0; j < D; ++j)
                 if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q, scale);
@@ -647,6 +677,7 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
 // float conversion; the factor scale * 2^24 is applied once per document (oracle: doc_score_vbyte).
 struct RecVB {
     static constexpr bool VBYTE = true;
+    static constexpr bool PLAIN_F16 = false;
     static constexpr int UNIT_BYTES = 16;
 };
 template <class R>
@@ -940,8 +971,15 @@ struct SmemHeap {
 // T threads per CTA, OCC = CTAs per SM the register allocation is budgeted for, D = documents per 8-lane group
 // per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise),
 // R = record layout (Rec16: u16 components, Rec32: u32 components).
-template <int T, int OCC, int D, class Q, class H, class R = Rec16>
+// TMA = true (u16 / f16 layout, byte-index query, D = 2 only): the records are not gathered with per-lane 128-bit loads
+// but staged round by round into a per-warp shared-memory buffer by the TMA unit — one cp.async.bulk per document
+// and round (<= 256 contiguous bytes), completion on the warp's mbarrier.  The copy of the NEXT round (or of the next
+// documents' first round) is issued as soon as the lanes have moved the current round into registers, i.e. it runs
+// under the ~130 lookup / multiply-add instructions of the current round: one 2 KB stage per warp is a full double
+// buffer, and no warp ever waits for a global load with its registers tied up.
+template <int T, int OCC, int D, class Q, class H, class R = Rec16, bool TMA = false>
 __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
+    static_assert(!TMA || (D == 2 && R::PLAIN_F16 && Q::HAS_DOT8), "TMA staging: u16/f16 records, byte-index query, D = 2");
     constexpr int NW = T / 32;      // warps
     constexpr int GROUPS = T / 8;   // 8-lane groups
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -958,6 +996,15 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     float* scores = reinterpret_cast<float*>(p);          p += (size_t)a.buf_docs * 4;
     uint32_t* surv = reinterpret_cast<uint32_t*>(p);      p += (size_t)((a.buf_docs + 31) / 32) * 4;  // bit d: document d of the wave can still enter the heap
     uint16_t* perm = reinterpret_cast<uint16_t*>(p);  // scoring order -> wave slot (longest documents first)
+    p += (size_t)a.buf_docs * 2;
+    // TMA variant: per warp one 2 KB stage (128-byte aligned) and one mbarrier
+    const uint32_t tma_ring_s = ((uint32_t)__cvta_generic_to_shared(p) + 127u) & ~127u;
+    __shared__ __align__(8) unsigned long long s_tma_bar[TMA ? NW : 1];
+    uint32_t tma_par = 0;  // parity of the warp's next mbarrier phase
+    if constexpr (TMA) {
+        if ((threadIdx.x & 31) == 0) mbar_init((uint32_t)__cvta_generic_to_shared(&s_tma_bar[threadIdx.x >> 5]), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     __shared__ uint32_t s_q;
     __shared__ uint4 s_vb_lut[is_vbyte<R>::value ? 256 : 1];  // DotVByte decode (vb_lut_entry); visible after the first barrier of the loop
@@ -1005,19 +1052,105 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
 
     // score docs[0, n) of the wave buffer into scores[] and mark the documents that can still enter the heap
     // nc > 0: also track the best surviving score of each of the wave's nc candidate blocks (cand_mx)
-    auto score_wave = [&](uint32_t n, uint32_t nc) {
-        auto note_survivor = [&](uint32_t d, float sc) {
-            atomicOr(&surv[d >> 5], 1u << (d & 31));
-            if (nc) {
-                uint32_t lo = 0, hi = nc - 1;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (cand_end[mid] <= d) lo = mid + 1;
-                    else hi = mid;
+    auto note_survivor = [&](uint32_t d, float sc, uint32_t nc) {
+        atomicOr(&surv[d >> 5], 1u << (d & 31));
+        if (nc) {
+            uint32_t lo = 0, hi = nc - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (cand_end[mid] <= d) lo = mid + 1;
+                else hi = mid;
+            }
+            atomicMax(&cand_mx[lo], total_key(sc));
+        }
+    };
+    // the TMA variant of score_wave (see the template comment): same results, records staged by bulk async copies
+    auto score_wave_tma = [&](uint32_t n, uint32_t nc) {
+        if constexpr (TMA) {
+        const bool w_full = s_full != 0;
+        const float w_theta = s_theta;
+        const uint32_t w_wkey = s_wkey;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_tma_bar[TMA ? warp : 0]);
+        const uint32_t stage = tma_ring_s + warp * TMA_WARP_BYTES + (lane >> 3) * 2 * TMA_ROUND_BYTES;  // this group's two rounds
+        const uint32_t sw = (lane8 >> 2) & 1u;
+        auto load_posts = [&](uint32_t dbase, uint64_t (&post)[2], uint32_t (&slot)[2]) -> uint32_t {
+            uint32_t mx = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t d = dbase + 2 * grp + j;
+                slot[j] = d < n ? perm[d] : 0xffffffffu;
+                post[j] = d < n ? docs[slot[j]] : 0ull;
+                mx = max(mx, (uint32_t)(post[j] & 0xffffu));
+            }
+            return max(1u, (__reduce_max_sync(0xffffffffu, mx) + 63) >> 6);  // >= 1: every iteration consumes one phase
+        };
+        auto issue = [&](const uint64_t (&post)[2], uint32_t r) {  // round r of the group's two documents
+            if (lane8 == 0) {
+                uint32_t bytes[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t total = (((uint32_t)(post[j] & 0xffffu) + 7) >> 3) * 32;
+                    bytes[j] = total > TMA_ROUND_BYTES * r ? min((uint32_t)TMA_ROUND_BYTES, total - TMA_ROUND_BYTES * r) : 0u;
                 }
-                atomicMax(&cand_mx[lo], total_key(sc));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was just read through the generic proxy
+                mbar_expect_tx(bar, bytes[0] + bytes[1]);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (bytes[j])
+                        tma_load_1d(stage + j * TMA_ROUND_BYTES,
+                                    reinterpret_cast<const char*>(a.ix.fwd) + (post[j] >> 16) * 32 + (size_t)TMA_ROUND_BYTES * r,
+                                    bytes[j], bar);
             }
         };
+        uint64_t post[2];
+        uint32_t slot[2];
+        uint32_t rounds = load_posts(0, post, slot);
+        issue(post, 0);
+        for (uint32_t dbase = 0; dbase < n; dbase += 2 * GROUPS) {  // CTA-uniform trip count
+            {   // the records after the next ones -> L2 (lane: document lane8 / 4, 128-byte lines lane8 % 4 and + 4)
+                const uint32_t dn = dbase + 4 * GROUPS + 2 * grp + (lane8 >> 2);
+                if (dn < n) {
+                    const uint64_t pn = docs[perm[dn]];
+                    const uint32_t bytes = rec_bytes(pn), ln = (lane8 & 3) * 128;
+                    const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pn >> 16) * 32;
+                    if (ln < bytes) prefetch_l2(base + ln);
+                    if (ln + 512 < bytes) prefetch_l2(base + ln + 512);
+                }
+            }
+            uint64_t post_n[2];
+            uint32_t slot_n[2];
+            const uint32_t rounds_n = load_posts(dbase + 2 * GROUPS, post_n, slot_n);
+            const uint32_t nch0 = ((uint32_t)(post[0] & 0xffffu) + 7) >> 3, nch1 = ((uint32_t)(post[1] & 0xffffu) + 7) >> 3;
+            float acc[2] = {0.f, 0.f};
+            for (uint32_t r = 0; r < rounds; ++r) {
+                const uint32_t m = lane8 + 8 * r;
+                mbar_wait(bar, tma_par);
+                tma_par ^= 1u;
+                uint4 c[2], v[2];
+                c[0] = c[1] = v[0] = v[1] = make_uint4(0, 0, 0, 0);
+                const uint32_t at = stage + 32 * lane8 + 16 * sw;
+                if (m < nch0) c[0] = lds128(at), v[0] = lds128(at ^ 16u);
+                if (m < nch1) c[1] = lds128(at + TMA_ROUND_BYTES), v[1] = lds128((at + TMA_ROUND_BYTES) ^ 16u);
+                __syncwarp();  // every lane holds its chunks in registers: the stage is free
+                if (r + 1 < rounds) issue(post, r + 1);
+                else if (dbase + 2 * GROUPS < n) issue(post_n, 0);
+                query.dot2x(acc[0], acc[1], c, v);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float sc = group_reduce(acc[j]);
+                const uint32_t d = slot[j];
+                if (lane8 == 0 && d != 0xffffffffu && (post[j] & 0xffffu)) {
+                    scores[d] = sc;
+                    st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
+                    if (!w_full || better(sc, (uint32_t)(post[j] >> 16), w_theta, w_wkey)) note_survivor(d, sc, nc);
+                }
+            }
+            post[0] = post_n[0], post[1] = post_n[1], slot[0] = slot_n[0], slot[1] = slot_n[1], rounds = rounds_n;
+        }
+            }
+    };
+    auto score_wave_ldg = [&](uint32_t n, uint32_t nc) {
         const bool w_full = s_full != 0;
         const float w_theta = s_theta;
         const uint32_t w_wkey = s_wkey;
@@ -1059,10 +1192,14 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     scores[d] = s;
                     if constexpr (!is_vbyte<R>::value) st_units += ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
                     // theta only grows: a document that cannot enter the heap as of the wave start never will
-                    if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey)) note_survivor(d, s);
+                    if (!w_full || better(s, (uint32_t)(post[j] >> 16), w_theta, w_wkey)) note_survivor(d, s, nc);
                 }
             }
         }
+    };
+    auto score_wave = [&](uint32_t n, uint32_t nc) {
+        if constexpr (TMA) score_wave_tma(n, nc);
+        else score_wave_ldg(n, nc);
     };
     // Fill the wave buffer with n postings (loader(i) = posting of slot i) and fix the scoring order.  A warp scores
     // 4 * D documents at a time (8 consecutive positions of the order) and every lane walks ceil(nnz / 64) rounds of

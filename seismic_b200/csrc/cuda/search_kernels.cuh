@@ -10,6 +10,7 @@ enum QueryKind { Q_DENSE = 0, Q_BYTE = 1, Q_HASH = 2, Q_RANK = 3, Q_SORTED = 4 }
 
 // u16 components, f16 values (the benchmark layout): every query representation
 kern_t pick_rec16(QueryKind q, bool small_k);
+kern_t pick_rec16_tma(bool small_k);  // Q_BYTE with TMA-staged records (k_search<..., TMA = true>)
 // u32 components, f16 values (SeismicIndexLV): Q_RANK, Q_SORTED
 kern_t pick_rec32(QueryKind q, bool small_k);
 // DotVByte: Q_BYTE, Q_SORTED

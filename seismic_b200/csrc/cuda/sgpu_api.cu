@@ -93,6 +93,7 @@ struct SgpuIndex {
     int hq_cand_cap = 256;    // candidate blocks per wave of the compact kernel
     int hq_carveout_pct = 0;  // shared-memory carveout of the compact kernel in % of the SM maximum (0: smallest that fits)
     int bucket = 1;   // score the documents of a wave longest first (uniform rounds per warp)
+    int tma = 0;      // u16/f16 layout, byte-index query: stage the records with TMA bulk copies (3 CTAs / SM)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
     // per-batch scratch (grow-only)
@@ -514,7 +515,9 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         ah.qd_words = ((ix->ix.dim + 127u) / 128u) * 4u;
         qbytes = 1024 + (size_t)ah.qd_words * 5;
     }
-    if (plain16) kh = pick_rec16(qk, small_k);
+    const bool use_tma = plain16 && qk == Q_BYTE && ix->tma;
+    if (use_tma) kh = pick_rec16_tma(small_k);
+    else if (plain16) kh = pick_rec16(qk, small_k);
     else if (vkind == SGPU_VAL_DOTVBYTE) kh = pick_vb(qk, small_k), kl = pick_vb(Q_SORTED, small_k);
     else if (comp32 && vkind == SGPU_VAL_F16) kh = pick_rec32(qk, small_k), kl = pick_rec32(Q_SORTED, small_k);
     else if (comp32) kh = pick_rec32v(vkind, qk, small_k), kl = pick_rec32v(vkind, Q_SORTED, small_k);
@@ -524,8 +527,8 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         return SGPU_EUNSUPPORTED;
     }
     ah.cand_cap = (uint32_t)std::min(hq_threads, std::max(32, ((ix->hq_cand_cap + 3) / 4) * 4));
-    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah);
-    bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 ? ix->smem_optin : ix->smem_optin / 2);
+    const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah) + (use_tma ? (size_t)(hq_threads / 32) * TMA_WARP_BYTES + 128 : 0);
+    bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 || use_tma ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
     uint32_t ctas_per_sm = 0;
     if (hq_ok) {
@@ -789,6 +792,10 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     }
     if (n == "bucket") {
         ix->bucket = value != 0;
+        return SGPU_OK;
+    }
+    if (n == "tma") {
+        ix->tma = value != 0;
         return SGPU_OK;
     }
     if (n == "hq_carveout_pct") {  // 0 = automatic

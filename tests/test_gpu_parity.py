@@ -375,3 +375,19 @@ def test_group_entry_single_and_multi_device(oracle_mod, synth_pruned):
         with pytest.raises(ValueError):
             g.batch_search(np.array([0, 2], np.uint64), np.array([9, 3], np.uint32), np.ones(2, np.float32), 10, 3, 0.8)
         del g
+
+
+@pytest.mark.parametrize("k,cut,hf,srt,wave", [(10, 3, 0.8, True, 768), (10, 5, 0.9, False, 768), (100, 4, 0.7, True, 64),
+                                               (1, 1000, 0.0, False, 1)])
+def test_tma_staged_records(oracle_mod, synth_pruned, synth_small, k, cut, hf, srt, wave):
+    """k_search<..., TMA = true>: the records are staged round by round into shared memory by cp.async.bulk + mbarrier
+    instead of per-lane 128-bit loads; results are identical (ids, score bits, evaluated blocks)."""
+    for docs, q, index in (synth_pruned, synth_small):
+        g = GpuIndex(index, 0)
+        g.set_option("tma", 1)
+        g.set_option("hq_wave_docs", wave)
+        g.set_option("hq_first_wave_docs", min(wave, 128))
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        assert_same(got, ref, f"tma k={k} cut={cut}")
+        assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"] and g.last_stats["ctas_per_sm"] >= 1

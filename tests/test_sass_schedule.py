@@ -30,10 +30,11 @@ def test_hot_loop_issues_all_gathers_before_the_first_lookup():
     assert start >= 0, "benchmark instantiation of k_search not found in the library"
     end = sass.find("Function : ", start + 10)
     ops = [m.group(1) for m in re.finditer(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", sass[start:end], re.M)]
-    first = next(i for i, o in enumerate(ops) if o.startswith("LDG.E.NA.128"))
+    is_gather = lambda o: re.match(r"LDG\.E(\.NA)?\.128\.CONSTANT", o) is not None  # noqa: E731  (ld.global.nc[.L1::no_allocate].v4)
+    first = next(i for i, o in enumerate(ops) if is_gather(o))
     gathers = 0
     for o in ops[first:]:
-        if o.startswith("LDG.E.NA.128"):
+        if is_gather(o):
             gathers += 1
         elif o.startswith("LDS.U8"):
             break

@@ -27,7 +27,7 @@ index = HostIndex.build(docs); del docs
 q = Dataset.synth_queries(cfg, a.queries)
 print("setup s", round(time.time() - t, 1), flush=True)
 gpu = GpuIndex(index, 0)
-defaults = {"hq_carveout_pct": 0, "hq_cand_cap": 256, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "bucket": 1}
+defaults = {"hq_carveout_pct": 0, "hq_cand_cap": 256, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "bucket": 1, "tma": 0}
 base = None
 rows = []
 for opt in a.opts:
