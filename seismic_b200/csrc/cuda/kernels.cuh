@@ -30,6 +30,7 @@
 //             src/utils.rs:12-66, src/inverted_index.rs:551-593) — search.cuh
 //   k_finish  key -> doc id (id_from_range, reference src/inverted_index.rs:227-233)
 #pragma once
+#include "summary.cuh"
 #include "types.cuh"
 
 namespace sgpu {
@@ -162,244 +163,36 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route(Scratch sc, uint32_t nq
 }
 
 // ------------------------------------------------------------------------------------------
-// k_est: Loop A.  One warp per (query, term), four independent warps per CTA.  est[s] accumulates, for the query
-// components present in the list's summaries IN ASCENDING COMPONENT ORDER, ((code * quant[s]) + min[s]) * qv with
-// four separate roundings (Rust does not contract to FMA).
-//
-// A task touches one to a few thousand summary entries (the list's own component alone occurs in almost every block
-// summary) and is bound by dependent memory round trips, not by bytes.  The addends do not depend on the accumulation
-// order, only the additions do, so a batch of up to 64 query components is handled in three steps: (1) every lane
-// searches two components in the list's sorted summary components (5-ary search: four independent probes per step,
-// then one 8-element probe) and fetches the run bounds; a warp scan lays the runs of the matched components end to
-// end; (2) the lanes walk that flat entry list, EST_U positions per lane and step, all loads of a step issued before
-// the first use — one memory latency covers 32 * EST_U entries instead of one run — and stage (block id, addend)
-// pairs in shared memory; (3) the staged pairs are added run by run (= component by component, ascending; a summary id
-// occurs at most once per component, so the lanes of one step never collide), __syncwarp() between runs.
-// The accumulators live in shared memory when the list has <= EST_SMEM blocks, else in the global scratch.
+// k_est / k_order: Loop A as stand-alone kernels (summary.cuh: est_task, order_task) — used for the queries that the
+// dense-query / sorted-query kernels take; k_search computes Loop A for its own queries inside its CTAs (`fuse_est`).
+// `skip_fused`: leave out the queries routed to the compact-query kernel (hmult != 0).
 // ------------------------------------------------------------------------------------------
 constexpr int EST_WARPS = 4;
 constexpr int EST_SMEM = 1024;  // blocks per warp kept in shared memory (4 KB); larger lists accumulate in global
 constexpr int EST_STAGE = 512;  // staged (block id, addend) pairs per warp and pass
-constexpr int EST_QB = 64;      // query components per batch (two per lane)
-constexpr int EST_U = 4;        // flat positions per lane and staging step
 
-// lower_bound(a[0, n), c): four independent probes per step, one aligned-size probe of up to 8 elements at the end
-__device__ __forceinline__ uint32_t lower_bound5(const uint32_t* __restrict__ a, uint32_t n, uint32_t c) {
-    uint32_t lo = 0, hi = n;
-    while (hi - lo > 8) {
-        const uint32_t st = (hi - lo + 4) / 5;  // five pieces of st elements; probe the last element of the first four
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t at = lo + (k + 1) * st - 1;
-            v[k] = at < hi ? __ldg(a + at) : 0xffffffffu;
-        }
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cnt += v[k] < c;
-        lo += cnt * st;
-        hi = min(hi, lo + st);
-    }
-    uint32_t v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = lo + k < hi ? __ldg(a + lo + k) : 0xffffffffu;
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) cnt += v[k] < c;
-    return lo + cnt;
-}
-
-__global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc) {
-    __shared__ float s_est[EST_WARPS][EST_SMEM];
-    __shared__ float s_add[EST_WARPS][EST_STAGE];
-    __shared__ uint16_t s_blk[EST_WARPS][EST_STAGE];
-    __shared__ uint32_t s_off[EST_WARPS][EST_QB + 1];  // first flat position of every component's run (exclusive scan)
-    __shared__ uint32_t s_e0[EST_WARPS][EST_QB];
-    __shared__ float s_qv[EST_WARPS][EST_QB];
-    __shared__ uint8_t s_own[EST_WARPS][EST_STAGE / 32];  // owner (component slot) of every 32nd position of the pass
+__global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc, int skip_fused) {
+    constexpr int SLICE = EST_STAGE * 6 + EST_AUX_BYTES + 16 + EST_SMEM * 4;
+    __shared__ __align__(16) unsigned char s_raw[EST_WARPS][SLICE];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t task = blockIdx.x * EST_WARPS + w;
     const uint32_t q = task / sc.cut_eff, t = task % sc.cut_eff;
     if (q >= b.nq || t >= sc.nterms[q]) return;  // warp-uniform; no block-wide barrier below
-    const uint32_t l = sc.terms[(uint64_t)q * sc.cut_eff + t];
-    const ListHdr h = ix.lists[l];
-    const uint32_t B = h.n_blk;
-    float* g_est = sc.est + ((uint64_t)q * sc.cut_eff + t) * sc.est_stride;
-    const bool in_smem = B <= EST_SMEM;
-    float* acc = in_smem ? s_est[w] : g_est;
-    for (uint32_t i = lane; i < B; i += 32) acc[i] = 0.f;
-    const uint64_t o = b.q_off[b.q_base + q];
-    const uint32_t n = (uint32_t)(b.q_off[b.q_base + q + 1] - o);
-    const uint32_t* scomp = ix.sc_comp + h.sc_base;
-    const uint32_t* skip = ix.sc_skip + h.skip_base;
-    const uint32_t n_skip = (h.n_sc + 31) >> 5;
-    const uint32_t* run = ix.sc_run_off + h.sc_base + l;
-    const uint16_t* eb = ix.ent_blk + h.ent_base;
-    const uint8_t* ec = ix.ent_code + h.ent_base;
-    const float* mins = ix.blk_min + h.blk_base;
-    const float* quants = ix.blk_quant + h.blk_base;
-    uint32_t* off = s_off[w];
-    uint32_t* e0s = s_e0[w];
-    float* qvs = s_qv[w];
-    float* st_add = s_add[w];
-    uint16_t* st_blk = s_blk[w];
-    uint8_t* own = s_own[w];
-    __syncwarp();
-    if (!in_smem) __threadfence_block();
-    for (uint32_t base = 0; base < n; base += EST_QB) {
-        // ---- (1) lane handles query components base + 2 * lane and base + 2 * lane + 1 (ascending across lanes)
-        uint32_t e0[2] = {0, 0}, len[2] = {0, 0};
-        float qv[2] = {0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const uint32_t i = base + 2 * lane + u;
-            if (i < n) {
-                const uint32_t c = b.q_comps[o + i];
-                qv[u] = b.q_vals[o + i];
-                if (!(i > 0 && b.q_comps[o + i - 1] == c)) {  // the merge consumes the first duplicate only
-                    // directory first (the 40 searches of a task share its ~16 sectors), then one group of 32
-                    const uint32_t g = lower_bound5(skip, n_skip, c);
-                    const uint32_t glen = g < n_skip ? min(32u, h.n_sc - 32 * g) : 0u;
-                    const uint32_t lo = 32 * g + lower_bound5(scomp + 32 * g, glen, c);
-                    if (g < n_skip && lo < h.n_sc && __ldg(scomp + lo) == c) {
-                        e0[u] = __ldg(run + lo);
-                        len[u] = __ldg(run + lo + 1) - e0[u];
-                    }
-                }
-            }
-        }
-        // flat entry list of the batch: exclusive prefix sum of the run lengths (slot 2 * lane + u)
-        const uint32_t mine = len[0] + len[1];
-        uint32_t incl = mine;
-#pragma unroll
-        for (int sft = 1; sft < 32; sft <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft);
-            if (lane >= (uint32_t)sft) incl += up;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        off[2 * lane] = incl - mine;
-        off[2 * lane + 1] = incl - mine + len[0];
-        e0s[2 * lane] = e0[0], e0s[2 * lane + 1] = e0[1];
-        qvs[2 * lane] = qv[0], qvs[2 * lane + 1] = qv[1];
-        if (lane == 0) off[EST_QB] = total;
-        __syncwarp();
-        for (uint32_t w0 = 0; w0 < total; w0 += EST_STAGE) {
-            const uint32_t w1 = min(total, w0 + EST_STAGE);
-            // owner of every 32nd position of the pass: last slot whose first position is <= p
-            if (lane * 32 < w1 - w0) {
-                const uint32_t p = w0 + lane * 32;
-                uint32_t j = 0;
-#pragma unroll
-                for (int step = EST_QB / 2; step > 0; step >>= 1)
-                    if (off[j + step] <= p) j += step;
-                own[lane] = (uint8_t)j;
-            }
-            __syncwarp();
-            // ---- (2) stage the addends of flat positions [w0, w1)
-            for (uint32_t p0 = w0; p0 < w1; p0 += 32 * EST_U) {
-                uint32_t pp[EST_U], ee[EST_U], ss[EST_U];
-                float wq[EST_U], code[EST_U], qn[EST_U], mn[EST_U];
-#pragma unroll
-                for (int u = 0; u < EST_U; ++u) {
-                    pp[u] = p0 + u * 32 + lane;
-                    if (pp[u] < w1) {
-                        uint32_t j = own[(pp[u] - w0) >> 5];
-                        while (off[j + 1] <= pp[u]) ++j;  // off[EST_QB] = total > p ends the walk
-                        ee[u] = e0s[j] + (pp[u] - off[j]);
-                        wq[u] = qvs[j];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < EST_U; ++u)
-                    if (pp[u] < w1) ss[u] = __ldg(eb + ee[u]), code[u] = (float)__ldg(ec + ee[u]);
-#pragma unroll
-                for (int u = 0; u < EST_U; ++u)
-                    if (pp[u] < w1) qn[u] = __ldg(quants + ss[u]), mn[u] = __ldg(mins + ss[u]);
-#pragma unroll
-                for (int u = 0; u < EST_U; ++u)
-                    if (pp[u] < w1) {
-                        st_blk[pp[u] - w0] = (uint16_t)ss[u];
-                        st_add[pp[u] - w0] = __fmul_rn(__fadd_rn(__fmul_rn(code[u], qn[u]), mn[u]), wq[u]);
-                    }
-            }
-            __syncwarp();
-            // ---- (3) add, one run (= one component) at a time, in ascending component order
-            for (uint32_t j = 0; j < EST_QB; ++j) {
-                const uint32_t r0 = off[j], r1 = off[j + 1];
-                if (r1 <= w0 || r0 >= w1 || r0 == r1) continue;  // warp-uniform
-                const uint32_t a0 = max(r0, w0), a1 = min(r1, w1);
-                for (uint32_t p = a0 + lane; p < a1; p += 32) {
-                    const uint32_t s = st_blk[p - w0];
-                    const float add = st_add[p - w0];
-                    if (in_smem) {
-                        acc[s] = __fadd_rn(acc[s], add);
-                    } else {
-                        const float cur = __ldcg(acc + s);
-                        __stcg(acc + s, __fadd_rn(cur, add));
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-    }
-    if (in_smem)
-        for (uint32_t i = lane; i < B; i += 32) g_est[i] = acc[i];
+    if (skip_fused && sc.hmult[q] != 0) return;
+    EstScratch es;
+    es.carve(s_raw[w], SLICE, EST_STAGE);
+    est_task(ix, b, sc, q, t, lane, es);
 }
 
-// ------------------------------------------------------------------------------------------
-// k_order: blocks of the FIRST list of each query sorted by (estimate desc under total_cmp, block id asc).
-// One CTA per query.  Bitonic sort of 64-bit composites in shared memory when B <= ORDER_SMEM, else a
-// rank sort straight from global memory (correct for any B <= 65535, slow; never hit by sane configs).
-// ------------------------------------------------------------------------------------------
 constexpr int ORDER_THREADS = 256;
 constexpr int ORDER_SMEM = 4096;
 
-__global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, Scratch sc) {
+__global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, Scratch sc, int skip_fused) {
     __shared__ uint64_t s_key[ORDER_SMEM];
     const uint32_t q = blockIdx.x;
     if (q >= b.nq || sc.nterms[q] == 0) return;
-    const uint32_t l = sc.terms[(uint64_t)q * sc.cut_eff];
-    const uint32_t B = ix.lists[l].n_blk;
-    const float* est = sc.est + (uint64_t)q * sc.cut_eff * sc.est_stride;
-    uint4* out = sc.sel + (uint64_t)q * sc.est_stride;
-    const uint32_t* boff = ix.blk_post_off + ix.lists[l].blk_base + l;
-    // the search kernel reads one 16-byte entry per position: no dependent order -> estimate -> offsets chain
-    auto emit = [&](uint32_t pos, uint32_t blk) {
-        const uint32_t p0 = boff[blk];
-        out[pos] = make_uint4(__float_as_uint(est[blk]), p0, boff[blk + 1] - p0, blk);
-    };
-    if (B <= ORDER_SMEM) {
-        uint32_t n2 = 1;
-        while (n2 < B) n2 <<= 1;
-        // ascending sort of ((~key) << 32 | id): smallest composite == largest estimate, then smallest id
-        for (uint32_t i = threadIdx.x; i < n2; i += ORDER_THREADS)
-            s_key[i] = i < B ? (((uint64_t)(~total_key(est[i])) << 32) | i) : ~0ull;
-        __syncthreads();
-        // thread t owns elements t, t + 256, ...: for j < 32 both partners of an exchange belong to the same warp
-        // (same 32-aligned group of elements), so only the steps with j >= 32 need a block-wide barrier
-        for (uint32_t ksz = 2; ksz <= n2; ksz <<= 1)
-            for (uint32_t j = ksz >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = threadIdx.x; i < n2; i += ORDER_THREADS) {
-                    uint32_t p = i ^ j;
-                    if (p > i) {
-                        uint64_t a = s_key[i], c = s_key[p];
-                        bool up = (i & ksz) == 0;
-                        if ((a > c) == up) s_key[i] = c, s_key[p] = a;
-                    }
-                }
-                if (j >= 32 || j == 1 && (ksz << 1) > 32) __syncthreads();  // also before the next step's wide exchange
-                else __syncwarp();
-            }
-        for (uint32_t i = threadIdx.x; i < B; i += ORDER_THREADS) emit(i, (uint32_t)(s_key[i] & 0xffffu));
-    } else {
-        for (uint32_t i = threadIdx.x; i < B; i += ORDER_THREADS) {
-            const uint64_t mine = ((uint64_t)(~total_key(est[i])) << 32) | i;
-            uint32_t rank = 0;
-            for (uint32_t j = 0; j < B; ++j) rank += ((((uint64_t)(~total_key(est[j])) << 32) | j) < mine);
-            emit(rank, i);
-        }
-    }
+    if (skip_fused && sc.hmult[q] != 0) return;
+    order_task<ORDER_THREADS>(ix, sc, q, threadIdx.x, s_key, ORDER_SMEM);
 }
 
 // ------------------------------------------------------------------------------------------

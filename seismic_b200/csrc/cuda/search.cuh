@@ -1278,6 +1278,10 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         heap.reset(k, heap_s, heap_k);
         if (tid == 0) s_full = 0, s_theta = 0.f, s_wkey = 0;
         __syncthreads();
+        // (Loop A — summary estimates and the first list's block order — was also run INSIDE this kernel's CTAs, one warp
+        // per list in the idle wave buffers, to hide its DRAM round trips under the other CTAs' scoring: measured 6.06
+        // vs 5.68 ms per 10 k queries at cut 3, 7.56 vs 6.65 at cut 5 — the CTA holds a quarter of the SM for the 21-28 %
+        // of its time the dependent loads take.  Dropped; the stand-alone k_est / k_order stay.)
         lap(0);
 
         bool first_wave = true;
@@ -1302,10 +1306,10 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 float e = 0.f;
                 if (pos < B) {  // independent loads: one memory round trip per selection pass
                     if (sel) {
-                        const uint4 se = sel[pos];
+                        const uint4 se = __ldcg(sel + pos);
                         e = __uint_as_float(se.x), p0 = se.y, nd = se.z;
                     } else {
-                        e = est[pos];
+                        e = __ldcg(est + pos);
                         p0 = boff[pos];
                         nd = boff[pos + 1] - p0;
                     }

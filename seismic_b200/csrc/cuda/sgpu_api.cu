@@ -627,11 +627,12 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         pd.launches += 2;
         CK(cudaEventRecord(ix->ev[3], st));
         const uint64_t tasks = (uint64_t)n * cut_eff;
-        k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc);
+        const int skip_fused = 0;
+        k_est<<<(unsigned)((tasks + EST_WARPS - 1) / EST_WARPS), EST_WARPS * 32, 0, st>>>(ix->ix, b, sc, skip_fused);
         CK(cudaGetLastError());
         ++pd.launches;
         if (ad.first_sorted) {
-            k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc);
+            k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc, skip_fused);
             CK(cudaGetLastError());
             ++pd.launches;
         }
@@ -798,6 +799,7 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
         ix->tma = value != 0;
         return SGPU_OK;
     }
+
     if (n == "hq_carveout_pct") {  // 0 = automatic
         ix->hq_carveout_pct = (int)std::min<int64_t>(100, std::max<int64_t>(0, value));
         return SGPU_OK;
