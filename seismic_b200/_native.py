@@ -16,7 +16,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 REPO = ROOT.parent
 LIB_DIR = ROOT / "_lib"
-LIB_PATH = LIB_DIR / "libseismic_b200.so"
+LIB_PATH = LIB_DIR / "libseismic_b200.so"      # the product: CUDA kernels + C ABI (sgpu_*) + the host side (shost_*)
+HOST_LIB_PATH = LIB_DIR / "libshost_b200.so"   # the host side alone (dataset, CPU index build, I/O, generator): no CUDA
 HOST_SRC = sorted((ROOT / "csrc" / "host").glob("*.cpp"))
 CUDA_SRC = sorted((ROOT / "csrc" / "cuda").glob("*.cu"))  # sgpu_api.cu + one translation unit per group of k_search instantiations
 HEADERS = (
@@ -33,9 +34,9 @@ NVCC_FLAGS = [
 
 
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not HOST_LIB_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
+    t = min(LIB_PATH.stat().st_mtime, HOST_LIB_PATH.stat().st_mtime)
     return any(p.stat().st_mtime > t for p in HOST_SRC + CUDA_SRC + HEADERS)
 
 
@@ -76,6 +77,17 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     os.replace(tmp, LIB_PATH)
+    # the host-only library: what the CPU legs (reference arm of bench.py, index construction) load — they never map
+    # the CUDA code
+    tmp = LIB_DIR / (".build_host_%d.so" % os.getpid())
+    hobjs = [str(OBJ_DIR / (src.stem + ".o")) for src in HOST_SRC]
+    cmd = [os.environ.get("CXX", "g++"), "-shared", "-fPIC", "-pthread", "-o", str(tmp), *hobjs]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, HOST_LIB_PATH)
     return LIB_PATH
 
 
@@ -183,6 +195,30 @@ SYMBOLS = {
 }
 
 _lib = None
+_hlib = None
+
+
+def hlib() -> C.CDLL:
+    """The host-only library (shost_* + sgpu_last_error): datasets, CPU index build, index files, generator."""
+    global _hlib
+    if _hlib is not None:
+        return _hlib
+    if os.environ.get("SEISMIC_B200_LIB"):  # A/B runs with one foreign build: take everything from it
+        _hlib = lib()
+        return _hlib
+    if _stale():
+        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            build_native()
+        elif not HOST_LIB_PATH.exists():
+            raise ImportError("seismic_b200: native library %s is missing and nvcc is not available" % HOST_LIB_PATH)
+    handle = C.CDLL(str(HOST_LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        if name.startswith("shost_") or name == "sgpu_last_error":
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+    _hlib = handle
+    return handle
 
 
 def lib() -> C.CDLL:
@@ -221,10 +257,15 @@ class SeismicError(RuntimeError):
 _ERR = {-1: ValueError, -2: SeismicError, -3: MemoryError, -4: OSError, -5: NotImplementedError}
 
 
-def check(rc: int) -> None:
+def check(rc: int, host: bool = False) -> None:
+    """Raise for a non-zero status; `host`: the call went to the host-only library (its own error string)."""
     if rc != 0:
-        msg = lib().sgpu_last_error().decode("utf-8", "replace")
+        msg = (hlib() if host else lib()).sgpu_last_error().decode("utf-8", "replace")
         raise _ERR.get(rc, SeismicError)(msg or ("seismic_b200 error %d" % rc))
+
+
+def hcheck(rc: int) -> None:
+    check(rc, host=True)
 
 
 def ptr(a: np.ndarray) -> int:

@@ -29,7 +29,7 @@ class Dataset:
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            N.lib().shost_dataset_destroy(self._h)
+            N.hlib().shost_dataset_destroy(self._h)
             self._h = C.c_void_p(0)
 
     @staticmethod
@@ -40,7 +40,7 @@ class Dataset:
         if len(comps) != len(values) or int(offsets[-1]) != len(comps):
             raise ValueError("inconsistent CSR arrays")
         out = C.c_void_p()
-        N.check(N.lib().shost_dataset_create(len(offsets) - 1, dim, N.ptr(offsets), N.ptr(comps), N.ptr(values), C.byref(out)))
+        N.hcheck(N.hlib().shost_dataset_create(len(offsets) - 1, dim, N.ptr(offsets), N.ptr(comps), N.ptr(values), C.byref(out)))
         return Dataset(out.value)
 
     @staticmethod
@@ -53,16 +53,16 @@ class Dataset:
     @staticmethod
     def read_bin(path: str) -> "Dataset":
         out = C.c_void_p()
-        N.check(N.lib().shost_dataset_read_bin(str(path).encode(), C.byref(out)))
+        N.hcheck(N.hlib().shost_dataset_read_bin(str(path).encode(), C.byref(out)))
         return Dataset(out.value)
 
     def write_bin(self, path: str) -> None:
-        N.check(N.lib().shost_dataset_write_bin(self._h, str(path).encode()))
+        N.hcheck(N.hlib().shost_dataset_write_bin(self._h, str(path).encode()))
 
     @staticmethod
     def synth_config(n_docs: int, dim: int = 30522, seed: int = 20260517, n_topics: Optional[int] = None, **kw) -> N.SynthConfig:
         cfg = N.SynthConfig()
-        N.lib().shost_default_synth(C.byref(cfg))
+        N.hlib().shost_default_synth(C.byref(cfg))
         cfg.n_docs, cfg.dim, cfg.seed = n_docs, dim, seed
         # keep ~2150 documents per topic at every scale (4096 topics at 8.8 M documents)
         cfg.n_topics = n_topics if n_topics else int(min(4096, max(16, n_docs // 2150)))
@@ -73,38 +73,38 @@ class Dataset:
     @staticmethod
     def synth_documents(cfg: N.SynthConfig) -> "Dataset":
         out = C.c_void_p()
-        N.check(N.lib().shost_synth_documents(C.byref(cfg), C.byref(out)))
+        N.hcheck(N.hlib().shost_synth_documents(C.byref(cfg), C.byref(out)))
         return Dataset(out.value)
 
     @staticmethod
     def synth_queries(cfg: N.SynthConfig, n_queries: int) -> "Dataset":
         out = C.c_void_p()
-        N.check(N.lib().shost_synth_queries(C.byref(cfg), n_queries, C.byref(out)))
+        N.hcheck(N.hlib().shost_synth_queries(C.byref(cfg), n_queries, C.byref(out)))
         return Dataset(out.value)
 
     def __len__(self) -> int:
-        return int(N.lib().shost_dataset_len(self._h))
+        return int(N.hlib().shost_dataset_len(self._h))
 
     @property
     def dim(self) -> int:
-        return int(N.lib().shost_dataset_dim(self._h))
+        return int(N.hlib().shost_dataset_dim(self._h))
 
     @property
     def nnz(self) -> int:
-        return int(N.lib().shost_dataset_nnz(self._h))
+        return int(N.hlib().shost_dataset_nnz(self._h))
 
     # borrowed views (valid while `self` is alive)
     @property
     def offsets(self) -> np.ndarray:
-        return N.np_view(N.lib().shost_dataset_offsets(self._h), len(self) + 1, np.uint64)
+        return N.np_view(N.hlib().shost_dataset_offsets(self._h), len(self) + 1, np.uint64)
 
     @property
     def comps(self) -> np.ndarray:
-        return N.np_view(N.lib().shost_dataset_comps(self._h), self.nnz, np.uint32)
+        return N.np_view(N.hlib().shost_dataset_comps(self._h), self.nnz, np.uint32)
 
     @property
     def values(self) -> np.ndarray:
-        return N.np_view(N.lib().shost_dataset_values(self._h), self.nnz, np.float32)
+        return N.np_view(N.hlib().shost_dataset_values(self._h), self.nnz, np.float32)
 
     def vector(self, i: int) -> Tuple[np.ndarray, np.ndarray]:
         o = self.offsets
@@ -115,7 +115,7 @@ def make_config(n_postings=3500, centroid_fraction=0.1, min_cluster_size=2, summ
                 doc_cut=15, comp_bits=16, value_kind=N.VAL_F16, n_threads=0, **extra) -> N.BuildConfig:
     """ShostBuildConfig with the Python defaults of the reference (src/pylib/mod.rs:329)."""
     cfg = N.BuildConfig()
-    N.lib().shost_default_config(C.byref(cfg))
+    N.hlib().shost_default_config(C.byref(cfg))
     cfg.n_postings, cfg.centroid_fraction, cfg.min_cluster_size = n_postings, centroid_fraction, min_cluster_size
     cfg.summary_energy, cfg.max_fraction, cfg.doc_cut = summary_energy, max_fraction, doc_cut
     cfg.comp_bits, cfg.value_kind, cfg.n_threads = comp_bits, value_kind, n_threads
@@ -130,33 +130,33 @@ class HostIndex:
     def __init__(self, handle: int):
         self._h = C.c_void_p(handle)
         self._view = N.IndexView()
-        N.check(N.lib().shost_index_view(self._h, C.byref(self._view)))
+        N.hcheck(N.hlib().shost_index_view(self._h, C.byref(self._view)))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
-            N.lib().shost_index_destroy(self._h)
+            N.hlib().shost_index_destroy(self._h)
             self._h = C.c_void_p(0)
 
     @staticmethod
     def build(dataset: Dataset, config: Optional[N.BuildConfig] = None, **params) -> "HostIndex":
         cfg = config if config is not None else make_config(**params)
         out = C.c_void_p()
-        N.check(N.lib().shost_index_build(dataset._h, C.byref(cfg), C.byref(out)))
+        N.hcheck(N.hlib().shost_index_build(dataset._h, C.byref(cfg), C.byref(out)))
         return HostIndex(out.value)
 
     @staticmethod
     def load(path: str) -> "HostIndex":
         out = C.c_void_p()
-        N.check(N.lib().shost_index_load(str(path).encode(), C.byref(out)))
+        N.hcheck(N.hlib().shost_index_load(str(path).encode(), C.byref(out)))
         return HostIndex(out.value)
 
     def save(self, path: str) -> None:
-        N.check(N.lib().shost_index_save(self._h, str(path).encode()))
+        N.hcheck(N.hlib().shost_index_save(self._h, str(path).encode()))
 
     def convert_to_dotvbyte(self) -> "HostIndex":
         """Same posting lists over a DotVByte forward index (reference src/pylib/dotvbyte.rs:195-213)."""
         out = C.c_void_p()
-        N.check(N.lib().shost_index_convert_dotvbyte(self._h, C.byref(out)))
+        N.hcheck(N.hlib().shost_index_convert_dotvbyte(self._h, C.byref(out)))
         return HostIndex(out.value)
 
     # -- kNN graph (reference Knn{n_vecs, dim, neighbours}, src/inverted_index.rs:430-434)
@@ -194,7 +194,7 @@ class HostIndex:
 
     @property
     def nnz(self) -> int:
-        return int(N.lib().shost_index_nnz(self._h))
+        return int(N.hlib().shost_index_nnz(self._h))
 
     @property
     def comp_bits(self) -> int:
@@ -202,7 +202,7 @@ class HostIndex:
 
     def space_usage(self) -> dict:
         b = (C.c_uint64 * 6)()
-        N.check(N.lib().shost_index_space_usage(self._h, b))
+        N.hcheck(N.hlib().shost_index_space_usage(self._h, b))
         return dict(zip(["forward", "packed_postings", "block_offsets", "summaries", "knn", "total"], map(int, b)))
 
     def get_doc(self, i: int) -> Tuple[np.ndarray, np.ndarray]:
@@ -210,7 +210,7 @@ class HostIndex:
         comps = np.empty(cap, np.uint32)
         vals = np.empty(cap, np.float32)
         n = C.c_uint32()
-        N.check(N.lib().shost_index_get_doc(self._h, i, N.ptr(comps), N.ptr(vals), cap, C.byref(n)))
+        N.hcheck(N.hlib().shost_index_get_doc(self._h, i, N.ptr(comps), N.ptr(vals), cap, C.byref(n)))
         return comps[: n.value].copy(), vals[: n.value].copy()
 
     def forward_csr(self, lo: int = 0, hi: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

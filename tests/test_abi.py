@@ -87,3 +87,21 @@ def test_group_entry_fails_loudly_without_gpu(native, synth_small):
     if not torch.cuda.is_available():
         with pytest.raises(native.SeismicError):
             GpuGroup(index, [0])
+
+
+def test_cpu_legs_do_not_map_the_product_library():
+    """Datasets, the CPU index build and index files live in libshost_b200.so: a process that only uses them (the
+    reference arm of bench.py, the oracle's callers) never maps the CUDA library."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from seismic_b200 import Dataset, HostIndex\n"
+        "cfg = Dataset.synth_config(2000, dim=500)\n"
+        "idx = HostIndex.build(Dataset.synth_documents(cfg), n_postings=100)\n"
+        "q = Dataset.synth_queries(cfg, 4)\n"
+        "import oracle; oracle.batch_search(idx.view, q.offsets, q.comps, q.values, 5, 3, 0.8)\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "print('libseismic_b200.so' in maps, 'libshost_b200.so' in maps)\n" % str(REPO))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["False", "True"], out
