@@ -1,9 +1,10 @@
 #include "search_kernels.cuh"
 #include "exact.cuh"
 namespace sgpu {
-kern_t pick_rec32(QueryKind q, bool small_k) {
+kern_t pick_rec32_occ(int hk, int occ);  // inst_rec32_b.cu
+kern_t pick_rec32(QueryKind q, int hk, int occ) {
     switch (q) {
-        case Q_RANK: return SGPU_K(256, 4, RankQuery, Rec32);
+        case Q_RANK: return occ == 4 ? SGPU_K3(256, 4, RankQuery, Rec32) : pick_rec32_occ(hk, occ);
         case Q_SORTED: return SGPU_K(256, 4, SortedQuery, Rec32);
         default: return nullptr;
     }

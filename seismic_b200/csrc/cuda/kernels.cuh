@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(ROUTE_THREADS) k_route(Scratch sc, uint32_t nq
 constexpr int EST_WARPS = 4;
 constexpr int EST_SMEM = 1024;  // blocks per warp kept in shared memory (4 KB); larger lists accumulate in global
 constexpr int EST_STAGE = 512;  // staged (block id, addend) pairs per warp and pass
+// (Builds with less staging and more resident warps — 256 pairs / 640 accumulators at 8 or 10 CTAs per SM, 128 / 640 at
+// 12 — were measured against this one, 6 CTAs per SM at 80 registers: 0.53 / 0.65 / 0.77 ms vs 0.51 ms for k_est +
+// k_order per 10 k queries at cut 3; the deep staging matters more than the occupancy.)
 
 __global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Scratch sc, int skip_fused) {
     constexpr int SLICE = EST_STAGE * 6 + EST_AUX_BYTES + 16 + EST_SMEM * 4;
@@ -186,13 +189,34 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_est(DevIndex ix, Batch b, Sc
 
 constexpr int ORDER_THREADS = 256;
 constexpr int ORDER_SMEM = 4096;
+constexpr uint32_t ORDER_WARP_MAX = 1024;
 
-__global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, Scratch sc, int skip_fused) {
+// `big_only`: only the queries whose first list has more than ORDER_WARP_MAX blocks (the others went to k_order_warp)
+__global__ void __launch_bounds__(ORDER_THREADS) k_order(DevIndex ix, Batch b, Scratch sc, int big_only) {
     __shared__ uint64_t s_key[ORDER_SMEM];
     const uint32_t q = blockIdx.x;
     if (q >= b.nq || sc.nterms[q] == 0) return;
-    if (skip_fused && sc.hmult[q] != 0) return;
+    if (big_only && ix.lists[sc.terms[(uint64_t)q * sc.cut_eff]].n_blk <= ORDER_WARP_MAX) return;
     order_task<ORDER_THREADS>(ix, sc, q, threadIdx.x, s_key, ORDER_SMEM);
+}
+
+// one warp per query, composites in registers (summary.cuh: order_warp); first lists of <= ORDER_WARP_MAX blocks.
+// BIG = false: lists of <= 512 blocks (<= 16 composites per lane); BIG = true: 513 .. 1024 blocks (32 per lane, a
+// separate kernel so that its 64 key registers do not set the occupancy of the common case).
+constexpr int ORDER_WARPS = 4;
+template <bool BIG>
+__global__ void __launch_bounds__(ORDER_WARPS * 32) k_order_warp(DevIndex ix, Batch b, Scratch sc) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * ORDER_WARPS + (threadIdx.x >> 5);
+    if (q >= b.nq || sc.nterms[q] == 0) return;  // warp-uniform
+    const uint32_t B = ix.lists[sc.terms[(uint64_t)q * sc.cut_eff]].n_blk;
+    if constexpr (BIG) {
+        if (B > 512 && B <= ORDER_WARP_MAX) order_warp<32>(ix, sc, q, lane);
+    } else {
+        if (B <= 128) order_warp<4>(ix, sc, q, lane);
+        else if (B <= 256) order_warp<8>(ix, sc, q, lane);
+        else if (B <= 512) order_warp<16>(ix, sc, q, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -353,6 +353,8 @@ struct RankQuery {
         acc = mac(acc, cw & 0xffffu, vw, false);
         return mac(acc, cw >> 16, vw, true);
     }
+    // (Fetching the 8 bitmap words of a chunk back to back before the hit tests, like ByteQuery::dot8, was measured on
+    // the large-vocabulary benchmark: 12.14 vs 11.97 ms per 10 k queries — no gain, dropped.)
     __device__ __forceinline__ float mac_f(float acc, uint32_t c, float val) const {
         const uint32_t w = bm[c >> 5];
         if ((w >> (c & 31)) & 1u) {
@@ -967,9 +969,95 @@ struct SmemHeap {
     }
 };
 
+// KHeap for 32 < k <= 128: the retained items UNSORTED in registers, four slots per lane (item i lives in slot i / 32 of
+// lane i % 32), scores as total_cmp keys, plus the current worst (theta, wkey).  A push overwrites the worst item and
+// finds the new worst with two warp reductions (minimum score key, then the largest record offset among the items that
+// have it) — ~45 instructions per change whatever k, against the ~150 dependent ones of a sorted shared-memory array
+// (at k = 100 a query changes its heap ~480 times).  Pushing a set of items one by one gives the k best of
+// (heap U set) in any order, and the order among the retained items is only needed once, for the output.
+// Scores are never -0.0 or NaN here (sums that start from +0.0), so the integer order equals `better`'s float order.
+struct WideHeap {
+    uint32_t tk[4], ky[4];  // per lane: total_key(score), key; empty slot = (0xffffffff, 0xffffffff)
+    uint32_t n, k, wkey, wtk;
+    float theta;
+    float* xs;  // k-entry buffers in shared memory (output sort)
+    uint32_t* xk;
+    __device__ __forceinline__ void reset(uint32_t kk, float* bs, uint32_t* bk) {
+        n = 0, k = kk, theta = 0.f, wkey = 0, wtk = 0, xs = bs, xk = bk;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) tk[r] = 0xffffffffu, ky[r] = 0xffffffffu;
+    }
+    __device__ __forceinline__ bool full() const { return n == k; }
+    static __device__ __forceinline__ bool btr(uint32_t t, uint32_t key, uint32_t wt, uint32_t wk) {
+        return t > wt || (t == wt && key < wk);
+    }
+    static __device__ __forceinline__ float untotal(uint32_t t) {
+        return __uint_as_float((t & 0x80000000u) ? (t & 0x7fffffffu) : ~t);
+    }
+    __device__ __forceinline__ void find_worst() {  // heap full: empty slots (k % 32 != 0) hold the largest key
+        wtk = __reduce_min_sync(0xffffffffu, min(min(tk[0], tk[1]), min(tk[2], tk[3])));
+        uint32_t lk = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) lk = max(lk, tk[r] == wtk ? ky[r] : 0u);
+        wkey = __reduce_max_sync(0xffffffffu, lk);
+        theta = untotal(wtk);
+    }
+    __device__ __forceinline__ void offer(bool have, const float sc, const uint32_t key, uint32_t lane, bool = true) {
+        const uint32_t ct = total_key(sc);
+        uint32_t m = __ballot_sync(0xffffffffu, have && (n < k || btr(ct, key, wtk, wkey)));
+        while (m) {  // warp-uniform: one candidate at a time against the live worst
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t bt = __shfl_sync(0xffffffffu, ct, src), bk = __shfl_sync(0xffffffffu, key, src);
+            if (n == k && !btr(bt, bk, wtk, wkey)) continue;
+            if (__any_sync(0xffffffffu, ky[0] == bk || ky[1] == bk || ky[2] == bk || ky[3] == bk)) continue;  // retained
+            if (n < k) {
+                const uint32_t r = n >> 5;
+                if (lane == (n & 31u)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (r == (uint32_t)j) tk[j] = bt, ky[j] = bk;
+                }
+                if (++n == k) find_worst();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (tk[j] == wtk && ky[j] == wkey) tk[j] = bt, ky[j] = bk;
+                find_worst();
+            }
+        }
+    }
+    __device__ __forceinline__ void store_keys(uint32_t* dst, uint32_t lane) const {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r * 32 + lane < n) dst[r * 32 + lane] = ky[r];
+    }
+    // best first: every item's position is the number of retained items that beat it (keys are distinct)
+    __device__ __forceinline__ void write_sorted(uint32_t lane, uint32_t* out_keys, float* out_scores) const {
+        uint32_t* xt = reinterpret_cast<uint32_t*>(xs);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r * 32 + lane < n) xt[r * 32 + lane] = tk[r], xk[r * 32 + lane] = ky[r];
+        __syncwarp();
+        uint32_t rank[4] = {0, 0, 0, 0};
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t jt = xt[j], jk = xk[j];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) rank[r] += btr(jt, jk, tk[r], ky[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (r * 32 + lane < n) out_keys[rank[r]] = ky[r], out_scores[rank[r]] = untotal(tk[r]);
+        for (uint32_t i = n + lane; i < k; i += 32) out_keys[i] = 0xffffffffu, out_scores[i] = -INFINITY;
+        __syncwarp();
+    }
+};
+
 // -----------------------------------------------------------------------------------------------------------
 // T threads per CTA, OCC = CTAs per SM the register allocation is budgeted for, D = documents per 8-lane group
-// per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, SmemHeap otherwise),
+// per scoring iteration, Q = query representation, H = heap (RegHeap for k <= 32, WideHeap for k <= 128 on the
+// benchmark layouts, SmemHeap otherwise),
 // R = record layout (Rec16: u16 components, Rec32: u32 components).
 // TMA = true (u16 / f16 layout, byte-index query, D = 2 only): the records are not gathered with per-lane 128-bit loads
 // but staged round by round into a per-warp shared-memory buffer by the TMA unit — one cp.async.bulk per document
@@ -983,6 +1071,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     constexpr int NW = T / 32;      // warps
     constexpr int GROUPS = T / 8;   // 8-lane groups
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (*a.n_list == 0) return;  // nothing routed to this instantiation (uniform): skip the table initialisation
     Q query;
     query.template init<T>(smem_raw, a, threadIdx.x);
     unsigned char* p = smem_raw + ((Q::bytes(a) + 15) & ~(size_t)15);
@@ -1164,6 +1253,16 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pn >> 16) * R::UNIT_BYTES;
                     if (ln < bytes) prefetch_l2(base + ln);
                     if (ln + 512 < bytes) prefetch_l2(base + ln + 512);
+                }
+            }
+            if constexpr (D == 1) {  // same, one document per group: its 8 lanes take the lines lane8 and lane8 + 8
+                const uint32_t dn = dbase + GROUPS + grp;
+                if (dn < n) {
+                    const uint64_t pn = docs[perm[dn]];
+                    const uint32_t bytes = rec_bytes(pn), ln = lane8 * 128;
+                    const char* base = reinterpret_cast<const char*>(a.ix.fwd) + (pn >> 16) * R::UNIT_BYTES;
+                    if (ln < bytes) prefetch_l2(base + ln);
+                    if (ln + 1024 < bytes) prefetch_l2(base + ln + 1024);
                 }
             }
             uint64_t post[D];

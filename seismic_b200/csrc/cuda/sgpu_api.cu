@@ -94,6 +94,10 @@ struct SgpuIndex {
     int hq_carveout_pct = 0;  // shared-memory carveout of the compact kernel in % of the SM maximum (0: smallest that fits)
     int bucket = 1;   // score the documents of a wave longest first (uniform rounds per warp)
     int tma = 0;      // u16/f16 layout, byte-index query: stage the records with TMA bulk copies (3 CTAs / SM)
+    int order_warp = 1;  // first-list block order by one warp per query in registers (0: CTA-wide shared-memory sort)
+    int wide_heap = 1;  // 32 < k <= 128: register heap (WideHeap) on the layouts that instantiate it (0: SmemHeap)
+    int occ16 = 4;      // u16 / f16 layout, byte-index query: kernel build (4 = two documents per group; 41, 51 = one)
+    int occ32 = 4;      // u32 / f16 layout (SeismicIndexLV): CTAs per SM the kernel's register budget is compiled for (4, 3, 2)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
     // per-batch scratch (grow-only)
@@ -190,6 +194,13 @@ int create_impl(const SgpuIndexView* v, int device, SgpuIndex** out) {
     CK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
     ix->smem_per_sm = (size_t)per_sm;
     ix->ctas = ix->n_sm;
+    if (comp32 && kind == SGPU_VAL_F16) {
+        // SeismicIndexLV: one document in flight per 8-lane group (48 registers, no spills), 5 CTAs per SM with
+        // slightly smaller waves (measured at 1 M docs, vocabulary 200 k, k = 100: 18.7 -> 11.4 ms per 10 k queries)
+        ix->occ32 = 51;
+        ix->hq_wave_docs = 640;
+        ix->hq_cand_cap = 128;
+    }
     CK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     ix->stream = ix->own_stream;
     for (auto& e : ix->ev) CK(cudaEventCreate(&e));
@@ -466,7 +477,7 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
     // table, <= 255 distinct components) and the kernel for longer queries (dense f32 query for the u16/f16 layout,
     // sorted-query binary search elsewhere)
     const size_t heap_bytes = 2 * (size_t)((k + 3) & ~3u) * 4;
-    const bool small_k = k <= 32;
+    const int hk = k <= 32 ? 0 : (k <= 128 && ix->wide_heap ? 1 : 2);  // heap kind (search_kernels.cuh)
     SearchArgs ad{};
     ad.ix = ix->ix;
     ad.k = k;
@@ -493,7 +504,7 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
     const uint32_t vkind = ix->ix.value_kind;
     const bool plain16 = !comp32 && vkind == SGPU_VAL_F16;  // the layout that also has the dense-query kernel
     const bool dense_ok = plain16 && smem_d + 1024 <= ix->smem_optin;
-    kern_t kd = pick_rec16(Q_DENSE, small_k);
+    kern_t kd = pick_rec16(Q_DENSE, hk);
     if (dense_ok) CK(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
 
     SearchArgs ah = ad;
@@ -516,17 +527,19 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         qbytes = 1024 + (size_t)ah.qd_words * 5;
     }
     const bool use_tma = plain16 && qk == Q_BYTE && ix->tma;
-    if (use_tma) kh = pick_rec16_tma(small_k);
-    else if (plain16) kh = pick_rec16(qk, small_k);
-    else if (vkind == SGPU_VAL_DOTVBYTE) kh = pick_vb(qk, small_k), kl = pick_vb(Q_SORTED, small_k);
-    else if (comp32 && vkind == SGPU_VAL_F16) kh = pick_rec32(qk, small_k), kl = pick_rec32(Q_SORTED, small_k);
-    else if (comp32) kh = pick_rec32v(vkind, qk, small_k), kl = pick_rec32v(vkind, Q_SORTED, small_k);
-    else kh = pick_rec16v(vkind, qk, small_k), kl = pick_rec16v(vkind, Q_SORTED, small_k);
+    if (use_tma) kh = pick_rec16_tma(hk);
+    else if (plain16) kh = qk == Q_BYTE && ix->occ16 != 4 ? pick_rec16_var(hk, ix->occ16) : pick_rec16(qk, hk);
+    else if (vkind == SGPU_VAL_DOTVBYTE) kh = pick_vb(qk, hk), kl = pick_vb(Q_SORTED, hk);
+    else if (comp32 && vkind == SGPU_VAL_F16) kh = pick_rec32(qk, hk, ix->occ32), kl = pick_rec32(Q_SORTED, hk, 4);
+    else if (comp32) kh = pick_rec32v(vkind, qk, hk), kl = pick_rec32v(vkind, Q_SORTED, hk);
+    else kh = pick_rec16v(vkind, qk, hk), kl = pick_rec16v(vkind, Q_SORTED, hk);
     if (!kh) {
         shost::set_error("no search kernel for this index layout");
         return SGPU_EUNSUPPORTED;
     }
     ah.cand_cap = (uint32_t)std::min(hq_threads, std::max(32, ((ix->hq_cand_cap + 3) / 4) * 4));
+    if (ad.n_knn > 0)  // Knn::refine snapshots the heap into the four candidate arrays
+        ah.cand_cap = (uint32_t)std::min<uint32_t>(hq_threads, std::max<uint32_t>(ah.cand_cap, ((k + 15) / 16) * 4));
     const size_t smem_h = ((qbytes + 15) & ~(size_t)15) + wave_bytes(ah) + (use_tma ? (size_t)(hq_threads / 32) * TMA_WARP_BYTES + 128 : 0);
     bool hq_ok = (!plain16 || ix->hq_enabled) && smem_h + 1024 <= (comp32 || use_tma ? ix->smem_optin : ix->smem_optin / 2);
     int hq_ctas = 0;
@@ -632,9 +645,21 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
         CK(cudaGetLastError());
         ++pd.launches;
         if (ad.first_sorted) {
-            k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc, skip_fused);
-            CK(cudaGetLastError());
-            ++pd.launches;
+            if (ix->order_warp) {
+                k_order_warp<false><<<(n + ORDER_WARPS - 1) / ORDER_WARPS, ORDER_WARPS * 32, 0, st>>>(ix->ix, b, sc);
+                CK(cudaGetLastError());
+                ++pd.launches;
+                if (ix->max_blocks > 512) {
+                    k_order_warp<true><<<(n + ORDER_WARPS - 1) / ORDER_WARPS, ORDER_WARPS * 32, 0, st>>>(ix->ix, b, sc);
+                    CK(cudaGetLastError());
+                    ++pd.launches;
+                }
+            }
+            if (!ix->order_warp || ix->max_blocks > ORDER_WARP_MAX) {
+                k_order<<<n, ORDER_THREADS, 0, st>>>(ix->ix, b, sc, ix->order_warp);
+                CK(cudaGetLastError());
+                ++pd.launches;
+            }
         }
         CK(cudaEventRecord(ix->ev[4], st));
         ad.b = ah.b = b;
@@ -797,6 +822,22 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     }
     if (n == "tma") {
         ix->tma = value != 0;
+        return SGPU_OK;
+    }
+    if (n == "order_warp") {
+        ix->order_warp = value != 0;
+        return SGPU_OK;
+    }
+    if (n == "wide_heap") {
+        ix->wide_heap = value != 0;
+        return SGPU_OK;
+    }
+    if (n == "occ16") {
+        ix->occ16 = (int)value;  // 4 (two documents per group), 41, 51 (one document per group, 4 / 5 CTAs per SM)
+        return SGPU_OK;
+    }
+    if (n == "occ32") {
+        ix->occ32 = (int)value;  // 4, 3, 2: CTAs / SM at two documents per group; 41, 51: one document per group
         return SGPU_OK;
     }
 

@@ -263,4 +263,72 @@ __device__ __forceinline__ void order_task(const DevIndex& ix, const Scratch& sc
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// order_warp<E>: the same order for a list of B <= 32 * E blocks, by ONE warp with the composites in registers
+// (element i = slot i / 32 of lane i % 32): bitonic network, exchanges at distance >= 32 stay inside a lane, the others
+// are one 64-bit shuffle — no shared memory, no barrier.  A third of the instructions of the CTA-wide version.
+// ------------------------------------------------------------------------------------------
+template <int E, int JJ>
+__device__ __forceinline__ void order_inlane(uint64_t (&key)[E], uint32_t ksz) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if ((e & JJ) == 0 && (e | JJ) < E) {
+            const uint64_t a = key[e], c = key[e | JJ];
+            const bool up = (((uint32_t)e << 5) & ksz) == 0;  // ksz >= 64 here: the direction bit is a slot bit
+            const bool sw = (a > c) == up;
+            key[e] = sw ? c : a;
+            key[e | JJ] = sw ? a : c;
+        }
+    }
+}
+template <int E>
+__device__ __forceinline__ void order_warp(const DevIndex& ix, const Scratch& sc, uint32_t q, uint32_t lane) {
+    const uint32_t l = sc.terms[(uint64_t)q * sc.cut_eff];
+    const uint32_t B = ix.lists[l].n_blk;
+    const float* est = sc.est + (uint64_t)q * sc.cut_eff * sc.est_stride;
+    uint4* out = sc.sel + (uint64_t)q * sc.est_stride;
+    const uint32_t* boff = ix.blk_post_off + ix.lists[l].blk_base + l;
+    uint64_t key[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t i = e * 32 + lane;
+        key[e] = i < B ? (((uint64_t)(~total_key(__ldcg(est + i))) << 32) | i) : ~0ull;
+    }
+    constexpr uint32_t N2 = 32 * E;
+    for (uint32_t ksz = 2; ksz <= N2; ksz <<= 1) {
+        for (uint32_t j = ksz >> 1; j >= 32; j >>= 1) {  // partner = another slot of the same lane
+            switch (j >> 5) {
+                case 16: order_inlane<E, 16>(key, ksz); break;
+                case 8: order_inlane<E, 8>(key, ksz); break;
+                case 4: order_inlane<E, 4>(key, ksz); break;
+                case 2: order_inlane<E, 2>(key, ksz); break;
+                default: order_inlane<E, 1>(key, ksz); break;
+            }
+        }
+        for (uint32_t j = min(ksz >> 1, 16u); j > 0; j >>= 1) {  // partner = the same slot of lane ^ j
+            const bool lower = (lane & j) == 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const uint64_t a = key[e];
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, a, j);
+                const bool up = ((((uint32_t)e << 5) | lane) & ksz) == 0;
+                const bool take_min = lower == up;
+                key[e] = ((o < a) == take_min) ? o : a;
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t pos = e * 32 + lane;
+        if (pos < B) {
+            const uint32_t blk = (uint32_t)(key[e] & 0xffffffffu);
+            const uint32_t t = ~(uint32_t)(key[e] >> 32);  // total_key of the estimate
+            const uint32_t bits = (t & 0x80000000u) ? (t & 0x7fffffffu) : ~t;
+            const uint32_t p0 = boff[blk];
+            out[pos] = make_uint4(bits, p0, boff[blk + 1] - p0, blk);
+        }
+    }
+}
+
 }  // namespace sgpu

@@ -391,3 +391,64 @@ def test_tma_staged_records(oracle_mod, synth_pruned, synth_small, k, cut, hf, s
         got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
         assert_same(got, ref, f"tma k={k} cut={cut}")
         assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"] and g.last_stats["ctas_per_sm"] >= 1
+
+
+@pytest.mark.parametrize("frac,lo,hi", [(0.03, 129, 256), (0.1, 513, 1024), (0.25, 1025, 2048), (0.5, 2049, 4096)])
+def test_first_list_order_size_classes(oracle_mod, frac, lo, hi):
+    """sort_and_search order of the first list (src/posting_list.rs:162-166): k_order_warp sorts lists of <= 512 and of
+    513..1024 blocks in registers (4 / 8 / 16 / 32 composites per lane), k_order the longer ones in shared memory — and
+    the old CTA-wide kernel (`order_warp = 0`) must give the same results on all of them.  The four corpora have lists
+    of up to 180, 599, 1493 and 2968 blocks (medians 84, 280, 701, 1396), so every size class is exercised."""
+    from conftest import build_synth
+    _, q, index = build_synth(20000, 200, dim=300, n_postings=3000, centroid_fraction=frac, max_fraction=2.0,
+                              min_cluster_size=0)
+    a = index.arrays()
+    mx = int(np.diff(a["list_blk_start"]).max())
+    assert lo <= mx <= hi, (frac, mx)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, 10, 4, 0.9, first_sorted=True)
+    g = GpuIndex(index, 0)
+    for ow in (1, 0):
+        g.set_option("order_warp", ow)
+        got = g.batch_search(q.offsets, q.comps, q.values, 10, 4, 0.9, first_sorted=True)
+        assert_same(got, ref, f"order_warp={ow} max blocks {mx}")
+        assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
+@pytest.mark.parametrize("k,cut,hf,srt", [(33, 3, 0.8, True), (100, 5, 0.9, True), (128, 4, 0.7, False), (64, 1000, 0.0, True)])
+def test_register_heap_for_k_up_to_128(oracle_mod, synth_pruned, synth_small, k, cut, hf, srt):
+    """KHeap for 32 < k <= 128 (src/utils.rs:12-66): WideHeap (unsorted, in registers, worst tracked by warp reductions)
+    against the oracle and against the sorted shared-memory heap (`wide_heap = 0`)."""
+    for docs, q, index in (synth_pruned, synth_small):
+        g = GpuIndex(index, 0)
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        for wide in (1, 0):
+            g.set_option("wide_heap", wide)
+            got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+            assert_same(got, ref, f"wide_heap={wide} k={k} cut={cut}")
+            assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
+@pytest.mark.parametrize("var", [41, 51])
+@pytest.mark.parametrize("k,cut,hf,srt", [(10, 3, 0.8, True), (100, 5, 0.9, False), (1, 1000, 0.0, True)])
+def test_one_document_per_group_builds(oracle_mod, synth_pruned, k, cut, hf, srt, var):
+    """k_search<256, OCC, D = 1, ...>: one document in flight per 8-lane group (4 or 5 CTAs per SM) — same results."""
+    _, q, index = synth_pruned
+    g = GpuIndex(index, 0)
+    g.set_option("occ16", var)
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+    assert_same(got, ref, f"occ16={var} k={k} cut={cut}")
+    assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
+@pytest.mark.parametrize("occ", [4, 41, 51, 3, 2])
+def test_large_vocabulary_kernel_builds(oracle_mod, synth_lv, occ):
+    """The u32-component kernel under its register budgets (`occ32`): identical results."""
+    _, q, index = synth_lv
+    g = GpuIndex(index, 0)
+    g.set_option("occ32", occ)
+    for k, cut, hf, srt in ((100, 5, 0.9, True), (10, 3, 0.8, False)):
+        ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
+        assert_same(got, ref, f"occ32={occ} k={k}")
+        assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]

@@ -18,16 +18,23 @@ ap.add_argument("--cut", type=int, default=3)
 ap.add_argument("--hf", type=float, default=0.8)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--out", default="gpurun_out/variants.json")
+ap.add_argument("--dim", type=int, default=30522)
+ap.add_argument("--comp-bits", type=int, default=16)
+ap.add_argument("--doc-nnz-mean", type=float, default=115.0)
+ap.add_argument("--dotvbyte", action="store_true")
+ap.add_argument("--check-oracle", type=int, default=0, help="compare the first N queries of the first option set with the CPU oracle")
 ap.add_argument("opts", nargs="+")
 a = ap.parse_args()
 
-cfg = Dataset.synth_config(a.docs)
+cfg = Dataset.synth_config(a.docs, dim=a.dim, doc_nnz_mean=a.doc_nnz_mean)
 t = time.time(); docs = Dataset.synth_documents(cfg)
-index = HostIndex.build(docs); del docs
+index = HostIndex.build(docs, comp_bits=a.comp_bits); del docs
+if a.dotvbyte:
+    index = index.convert_to_dotvbyte()
 q = Dataset.synth_queries(cfg, a.queries)
 print("setup s", round(time.time() - t, 1), flush=True)
 gpu = GpuIndex(index, 0)
-defaults = {"hq_carveout_pct": 0, "hq_cand_cap": 256, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "bucket": 1, "tma": 0}
+defaults = {"hq_carveout_pct": 0, "hq_cand_cap": 256, "hq_wave_docs": 768, "hq_first_wave_docs": 128, "bucket": 1, "tma": 0, "wide_heap": 1, "occ32": 4}
 base = None
 rows = []
 for opt in a.opts:
@@ -46,6 +53,14 @@ for opt in a.opts:
                 best = st
         if base is None:
             base = (ids.copy(), sc.copy(), cnt.copy())
+            if a.check_oracle:
+                import oracle
+                n = min(a.check_oracle, a.queries)
+                o = q.offsets[: n + 1]
+                ref = oracle.batch_search(index.view, o, q.comps[: int(o[-1])], q.values[: int(o[-1])], a.k, a.cut, a.hf,
+                                          first_sorted=True, n_threads=0)
+                print(json.dumps({"oracle_mismatch_first_%d" % n: int(((ids[:n] != ref[0]).any(axis=1) | (cnt[:n] != ref[2])).sum()),
+                                  "scores_equal": bool(np.array_equal(sc[:n], ref[1]))}), flush=True)
         same = bool(np.array_equal(ids, base[0]) and np.array_equal(sc.view(np.uint32), base[1].view(np.uint32))
                     and np.array_equal(cnt, base[2]))
         tot = float(sum(best["phase_cycles"])) or 1.0
