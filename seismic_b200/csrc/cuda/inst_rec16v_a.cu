@@ -7,8 +7,8 @@ kern_t pick_rec16v(uint32_t value_kind, QueryKind q, int hk) {
     if (q != Q_BYTE && q != Q_SORTED) return nullptr;
     const bool s = q == Q_SORTED;
     switch (value_kind) {
-        case SGPU_VAL_BF16: return s ? SGPU_K(256, 4, SortedQuery, Rec16V2<1>) : SGPU_K(256, 4, ByteQuery, Rec16V2<1>);
-        case SGPU_VAL_FIXEDU16: return s ? SGPU_K(256, 4, SortedQuery, Rec16V2<4>) : SGPU_K(256, 4, ByteQuery, Rec16V2<4>);
+        case SGPU_VAL_BF16: return s ? SGPU_K1(256, 4, SortedQuery, Rec16V2<1>) : SGPU_K1(256, 4, ByteQuery, Rec16V2<1>);
+        case SGPU_VAL_FIXEDU16: return s ? SGPU_K1(256, 4, SortedQuery, Rec16V2<4>) : SGPU_K1(256, 4, ByteQuery, Rec16V2<4>);
         default: return pick_rec16v_b(value_kind, q, hk);
     }
 }

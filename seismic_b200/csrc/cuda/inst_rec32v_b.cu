@@ -5,8 +5,8 @@ namespace sgpu {
 kern_t pick_rec32v_b(uint32_t value_kind, QueryKind q, int hk) {
     const bool s = q == Q_SORTED;
     switch (value_kind) {
-        case SGPU_VAL_F32: return s ? SGPU_K(256, 4, SortedQuery, Rec32V<2>) : SGPU_K(256, 4, RankQuery, Rec32V<2>);
-        case SGPU_VAL_FIXEDU8: return s ? SGPU_K(256, 4, SortedQuery, Rec32V<3>) : SGPU_K(256, 4, RankQuery, Rec32V<3>);
+        case SGPU_VAL_F32: return s ? SGPU_K1(256, 4, SortedQuery, Rec32V<2>) : SGPU_K1(256, 4, RankQuery, Rec32V<2>);
+        case SGPU_VAL_FIXEDU8: return s ? SGPU_K1(256, 4, SortedQuery, Rec32V<3>) : SGPU_K1(256, 4, RankQuery, Rec32V<3>);
         default: return nullptr;
     }
 }

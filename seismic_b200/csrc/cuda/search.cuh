@@ -203,6 +203,9 @@ struct ByteQuery {  // qidx[c] = 1 + position of c in the query (0 = absent); va
     }
     // One chunk of each of two documents in a single basic block: 16 independent index loads, then 16 value loads,
     // then the two (ordered) multiply-add chains — the shared-memory latency is paid twice per call, not per chunk.
+    // (The index loads are 67 % of the kernel's shared-memory wavefronts: 32 random bytes hit 2.9 banks-deep on average.
+    // Issuing every one of them twice — +61 % wavefronts, same results — costs +23 % kernel time, i.e. removing ALL of
+    // their bank conflicts would buy at most ~15 %: profiles/r2_exp_double_idx.log.)
     __device__ __forceinline__ void dot2x(float& a0, float& a1, const uint4 (&c)[2], const uint4 (&v)[2]) const {
         uint32_t idx[16];
         float q[16];
@@ -777,6 +780,9 @@ __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream
         }
         if constexpr (D == 2 && Q::HAS_DOT8) {
             q.dot2x(acc[0], acc[1], c, v);
+        } else if constexpr (Q::HAS_DOT8) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) acc[j] = q.dot8(acc[j], c[j], v[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < D; ++j) {

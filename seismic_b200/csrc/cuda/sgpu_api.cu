@@ -97,6 +97,7 @@ struct SgpuIndex {
     int order_warp = 1;  // first-list block order by one warp per query in registers (0: CTA-wide shared-memory sort)
     int wide_heap = 1;  // 32 < k <= 128: register heap (WideHeap) on the layouts that instantiate it (0: SmemHeap)
     int occ16 = 4;      // u16 / f16 layout, byte-index query: kernel build (4 = two documents per group; 41, 51 = one)
+    int occvb = 4;      // DotVByte layout: same choice
     int occ32 = 4;      // u32 / f16 layout (SeismicIndexLV): CTAs per SM the kernel's register budget is compiled for (4, 3, 2)
     int ctas = 0;
     uint64_t scratch_bytes = 1ull << 30;
@@ -529,7 +530,7 @@ int enqueue_search(SgpuIndex* ix, const SgpuQueryBatch* dq, const SgpuSearchPara
     const bool use_tma = plain16 && qk == Q_BYTE && ix->tma;
     if (use_tma) kh = pick_rec16_tma(hk);
     else if (plain16) kh = qk == Q_BYTE && ix->occ16 != 4 ? pick_rec16_var(hk, ix->occ16) : pick_rec16(qk, hk);
-    else if (vkind == SGPU_VAL_DOTVBYTE) kh = pick_vb(qk, hk), kl = pick_vb(Q_SORTED, hk);
+    else if (vkind == SGPU_VAL_DOTVBYTE) kh = pick_vb(qk, hk, ix->occvb), kl = pick_vb(Q_SORTED, hk, 4);
     else if (comp32 && vkind == SGPU_VAL_F16) kh = pick_rec32(qk, hk, ix->occ32), kl = pick_rec32(Q_SORTED, hk, 4);
     else if (comp32) kh = pick_rec32v(vkind, qk, hk), kl = pick_rec32v(vkind, Q_SORTED, hk);
     else kh = pick_rec16v(vkind, qk, hk), kl = pick_rec16v(vkind, Q_SORTED, hk);
@@ -834,6 +835,10 @@ int sgpu_index_set_option(SgpuIndex* ix, const char* name, int64_t value) {
     }
     if (n == "occ16") {
         ix->occ16 = (int)value;  // 4 (two documents per group), 41, 51 (one document per group, 4 / 5 CTAs per SM)
+        return SGPU_OK;
+    }
+    if (n == "occvb") {
+        ix->occvb = (int)value;
         return SGPU_OK;
     }
     if (n == "occ32") {
