@@ -155,6 +155,8 @@ uint64_t sgpu_index_device_bytes(const SgpuIndex* index);
  *   out_counts [n_queries]   number of valid results (the reference may return < k,
  *                            src/bin/perf_inverted_index.rs:201-206)
  * Results are returned in input order.
+ * Caller buffers that are page-locked (sgpu_host_alloc, cudaMallocHost, cudaHostRegister) are read / written by DMA
+ * directly; pageable ones are staged through the library's pinned buffers.
  */
 int sgpu_batch_search(SgpuIndex* index, const SgpuQueryBatch* queries, const SgpuSearchParams* params,
                       uint64_t* out_ids, float* out_scores, uint32_t* out_counts, SgpuSearchStats* stats);
@@ -206,6 +208,10 @@ int sgpu_group_set_knn(SgpuGroup* group, const uint64_t* neighbours, uint32_t kn
 int sgpu_group_batch_search(SgpuGroup* group, const SgpuQueryBatch* queries, const SgpuSearchParams* params,
                             uint64_t* out_ids, float* out_scores, uint32_t* out_counts, SgpuSearchStats* stats,
                             float* ms_gather);
+
+/* Page-locked host memory for query / result buffers (cudaHostAlloc); free with sgpu_host_free. */
+int sgpu_host_alloc(uint64_t bytes, void** out);
+void sgpu_host_free(void* p);
 
 const char* sgpu_last_error(void);
 /* "seismic_b200 <version> sm_100a" */

@@ -165,6 +165,8 @@ SYMBOLS = {
     "sgpu_group_set_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "sgpu_group_batch_search": (C.c_int, [C.c_void_p, C.POINTER(QueryBatch), C.POINTER(SearchParams), C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.POINTER(SearchStats), C.POINTER(C.c_float)]),
+    "sgpu_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "sgpu_host_free": (None, [C.c_void_p]),
     "sgpu_last_error": (C.c_char_p, []),
     "sgpu_version": (C.c_char_p, []),
     "shost_default_config": (None, [C.POINTER(BuildConfig)]),

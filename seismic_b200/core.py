@@ -307,15 +307,24 @@ class GpuIndex:
             raise ValueError("k must be > 0")
         return N.SearchParams(int(k), int(query_cut), float(heap_factor), int(n_knn), 1 if first_sorted else 0)
 
-    def batch_search(self, offsets, comps, values, k, query_cut, heap_factor, n_knn=0, first_sorted=True):
-        """Host buffers in, host buffers out (H2D/D2H inside the call). Returns ids[nq,k], scores[nq,k], counts[nq]."""
+    def batch_search(self, offsets, comps, values, k, query_cut, heap_factor, n_knn=0, first_sorted=True, out=None):
+        """Host buffers in, host buffers out (H2D/D2H inside the call). Returns ids[nq,k], scores[nq,k], counts[nq].
+        `out` = (ids, scores, counts) arrays to fill instead of fresh ones; page-locked arrays (`pinned_array`), for
+        inputs and outputs alike, are read / written by DMA without the staging copy."""
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         comps = np.ascontiguousarray(comps, dtype=np.uint32)
         values = np.ascontiguousarray(values, dtype=np.float32)
         nq = len(offsets) - 1
-        ids = np.empty((nq, k), dtype=np.uint64)
-        scores = np.empty((nq, k), dtype=np.float32)
-        counts = np.empty(nq, dtype=np.uint32)
+        if out is not None:
+            ids, scores, counts = out
+            if (ids.shape != (nq, k) or ids.dtype != np.uint64 or scores.shape != (nq, k) or scores.dtype != np.float32
+                    or counts.shape != (nq,) or counts.dtype != np.uint32
+                    or not (ids.flags.c_contiguous and scores.flags.c_contiguous and counts.flags.c_contiguous)):
+                raise ValueError("out = (uint64[nq,k], float32[nq,k], uint32[nq]) C-contiguous arrays")
+        else:
+            ids = np.empty((nq, k), dtype=np.uint64)
+            scores = np.empty((nq, k), dtype=np.float32)
+            counts = np.empty(nq, dtype=np.uint32)
         qb = N.QueryBatch(nq, N.ptr(offsets), N.ptr(comps), N.ptr(values))
         p = self._params(k, query_cut, heap_factor, n_knn, first_sorted)
         st = N.SearchStats()
@@ -391,6 +400,28 @@ class GpuGroup:
         self.last_stats = st.as_dict()
         self.last_stats["ms_gather"] = ms.value
         return ids, scores, counts
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        N.check(N.lib().sgpu_host_alloc(int(nbytes), C.byref(self.ptr)))
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            N.lib().sgpu_host_free(self.ptr)
+            self.ptr = C.c_void_p(0)
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """A numpy array in page-locked host memory (sgpu_host_alloc): the search calls DMA straight from / into it."""
+    dtype = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    block = _PinnedBlock(max(nbytes, 1))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(block.ptr.value)
+    buf._block = block  # the memory lives as long as any array derived from `buf`
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
 
 
 def recall_at_k(exact_ids: np.ndarray, exact_counts: np.ndarray, run_ids: np.ndarray, run_counts: np.ndarray) -> float:

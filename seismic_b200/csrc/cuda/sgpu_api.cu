@@ -69,6 +69,16 @@ struct PinnedBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// true for cudaMallocHost / cudaHostRegister memory (the DMA engine can read or write it directly)
+static bool is_page_locked(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 }  // namespace
 
 struct SgpuIndex {
@@ -891,23 +901,26 @@ int sgpu_batch_search(SgpuIndex* ix, const SgpuQueryBatch* q, const SgpuSearchPa
     if (nq == 0) return SGPU_OK;
     const uint64_t nnz = q->offsets[nq];
     cudaStream_t st = ix->stream;
-    // stage inputs through pinned memory so the copies are truly asynchronous DMA
+    // Inputs: page-locked caller buffers are copied by DMA as they are; pageable ones are staged through pinned memory
+    // piece by piece, so that the DMA of one array runs under the host copy of the next.
     const size_t b_off = (nq + 1) * 8, b_c = nnz * 4, b_v = nnz * 4;
     CK(ix->h_in.ensure(b_off + b_c + b_v));
     uint8_t* hin = ix->h_in.as<uint8_t>();
-    std::memcpy(hin, q->offsets, b_off);
-    if (nnz) {
-        std::memcpy(hin + b_off, q->comps, b_c);
-        std::memcpy(hin + b_off + b_c, q->values, b_v);
-    }
     CK(ix->d_qoff.ensure(b_off));
     CK(ix->d_qcomps.ensure(std::max<size_t>(b_c, 4)));
     CK(ix->d_qvals.ensure(std::max<size_t>(b_v, 4)));
-    CK(cudaMemcpyAsync(ix->d_qoff.p, hin, b_off, cudaMemcpyHostToDevice, st));
-    if (nnz) {
-        CK(cudaMemcpyAsync(ix->d_qcomps.p, hin + b_off, b_c, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ix->d_qvals.p, hin + b_off + b_c, b_v, cudaMemcpyHostToDevice, st));
-    }
+    auto upload = [&](void* dst, const void* src, uint8_t* stage, size_t bytes) -> int {
+        if (!bytes) return SGPU_OK;
+        if (!is_page_locked(src)) {
+            std::memcpy(stage, src, bytes);
+            src = stage;
+        }
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return SGPU_OK;
+    };
+    if (int rc = upload(ix->d_qoff.p, q->offsets, hin, b_off)) return rc;
+    if (int rc = upload(ix->d_qcomps.p, q->comps, hin + b_off, b_c)) return rc;
+    if (int rc = upload(ix->d_qvals.p, q->values, hin + b_off + b_c, b_v)) return rc;
     const size_t o_ids = nq * p->k * 8, o_sc = nq * p->k * 4, o_cnt = nq * 4;
     CK(ix->d_out_ids.ensure(o_ids));
     CK(ix->d_out_scores.ensure(o_sc));
@@ -917,12 +930,19 @@ int sgpu_batch_search(SgpuIndex* ix, const SgpuQueryBatch* q, const SgpuSearchPa
     if (int rc = enqueue_search(ix, &dq, p, ix->d_out_ids.as<uint64_t>(), ix->d_out_scores.as<float>(),
                                 ix->d_out_counts.as<uint32_t>(), pd))
         return rc;
-    CK(ix->h_out.ensure(o_ids + o_sc + o_cnt));
-    uint8_t* hout = ix->h_out.as<uint8_t>();
+    // Outputs: straight into page-locked caller buffers, else through the pinned staging buffer
+    const bool direct_out = is_page_locked(out_ids) && is_page_locked(out_scores) && is_page_locked(out_counts);
+    uint8_t* hout = nullptr;
+    if (!direct_out) {
+        CK(ix->h_out.ensure(o_ids + o_sc + o_cnt));
+        hout = ix->h_out.as<uint8_t>();
+    }
     auto copy_out = [&]() -> int {
-        CK(cudaMemcpyAsync(hout, ix->d_out_ids.p, o_ids, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hout + o_ids, ix->d_out_scores.p, o_sc, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hout + o_ids + o_sc, ix->d_out_counts.p, o_cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(direct_out ? (void*)out_ids : (void*)hout, ix->d_out_ids.p, o_ids, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(direct_out ? (void*)out_scores : (void*)(hout + o_ids), ix->d_out_scores.p, o_sc,
+                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(direct_out ? (void*)out_counts : (void*)(hout + o_ids + o_sc), ix->d_out_counts.p, o_cnt,
+                           cudaMemcpyDeviceToHost, st));
         return SGPU_OK;
     };
     if (int rc = copy_out()) return rc;
@@ -932,10 +952,26 @@ int sgpu_batch_search(SgpuIndex* ix, const SgpuQueryBatch* q, const SgpuSearchPa
         if (int rc = copy_out()) return rc;
         CK(cudaStreamSynchronize(st));
     }
-    std::memcpy(out_ids, hout, o_ids);
-    std::memcpy(out_scores, hout + o_ids, o_sc);
-    std::memcpy(out_counts, hout + o_ids + o_sc, o_cnt);
+    if (!direct_out) {
+        std::memcpy(out_ids, hout, o_ids);
+        std::memcpy(out_scores, hout + o_ids, o_sc);
+        std::memcpy(out_counts, hout + o_ids + o_sc, o_cnt);
+    }
     return SGPU_OK;
+}
+
+int sgpu_host_alloc(uint64_t bytes, void** out) {
+    if (!out) {
+        shost::set_error("sgpu_host_alloc: null argument");
+        return SGPU_EINVAL;
+    }
+    *out = nullptr;
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return SGPU_OK;
+}
+
+void sgpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int sgpu_exact_search(SgpuIndex* ix, const SgpuQueryBatch* q, uint32_t k, uint64_t* out_ids, float* out_scores,

@@ -452,3 +452,23 @@ def test_large_vocabulary_kernel_builds(oracle_mod, synth_lv, occ):
         got = g.batch_search(q.offsets, q.comps, q.values, k, cut, hf, first_sorted=srt)
         assert_same(got, ref, f"occ32={occ} k={k}")
         assert g.last_stats["blocks_pushed"] == ref[3]["blocks_evaluated"]
+
+
+def test_page_locked_caller_buffers(oracle_mod, synth_pruned, gpu_pruned):
+    """sgpu_batch_search reads page-locked query buffers and writes page-locked result buffers by DMA (no staging copy);
+    pageable buffers take the staged path — same results either way, also when the two kinds are mixed."""
+    from seismic_b200 import pinned_array
+    _, q, index = synth_pruned
+    nq, k = len(q.offsets) - 1, 10
+    ref = oracle_mod.batch_search(index.view, q.offsets, q.comps, q.values, k, 3, 0.8, first_sorted=True)
+    p_off, p_c, p_v = pinned_array(q.offsets.shape, np.uint64), pinned_array(q.comps.shape, np.uint32), pinned_array(q.values.shape, np.float32)
+    p_off[:], p_c[:], p_v[:] = q.offsets, q.comps, q.values
+    out = (pinned_array((nq, k), np.uint64), pinned_array((nq, k), np.float32), pinned_array(nq, np.uint32))
+    got = gpu_pruned.batch_search(p_off, p_c, p_v, k, 3, 0.8, first_sorted=True, out=out)
+    assert got[0] is out[0] and got[2] is out[2]
+    assert_same(got, ref, "pinned in, pinned out")
+    assert_same(gpu_pruned.batch_search(p_off, q.comps, p_v, k, 3, 0.8, first_sorted=True), ref, "mixed in, pageable out")
+    out2 = (np.empty((nq, k), np.uint64), np.empty((nq, k), np.float32), np.empty(nq, np.uint32))
+    assert_same(gpu_pruned.batch_search(q.offsets, q.comps, q.values, k, 3, 0.8, first_sorted=True, out=out2), ref, "pageable out=")
+    with pytest.raises(ValueError):
+        gpu_pruned.batch_search(q.offsets, q.comps, q.values, k, 3, 0.8, out=(out2[0][:, :5], out2[1], out2[2]))
