@@ -46,6 +46,9 @@ constexpr int DENSE_THREADS = 1024;
 #ifndef SGPU_DOT2X
 #define SGPU_DOT2X 1
 #endif
+#ifndef SGPU_SEL_P
+#define SGPU_SEL_P 2  // block positions per thread and selection pass of k_search
+#endif
 #ifndef SGPU_SKIP_MISS
 #define SGPU_SKIP_MISS 1
 #endif
@@ -1400,40 +1403,56 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             const uint64_t* posts = a.ix.postings + h.post_base;
             uint32_t pos0 = 0;
             while (pos0 < B) {
-                // ---------------- phase 1: candidate selection over positions [pos0, pos0 + T)
+                // ---------------- phase 1: candidate selection over positions [pos0, pos0 + SP * T), SP consecutive
+                // positions per thread (a list of the benchmark index has ~350 blocks: one pass instead of two)
+                constexpr int SP = SGPU_SEL_P;
                 if (tid == 0) ++s_cnt[1];
                 const bool full = s_full != 0;
                 const float thr = __fmul_rn(a.heap_factor, s_theta);
                 const uint32_t cap = first_wave ? a.first_wave_docs : a.wave_docs;
-                const uint32_t pos = pos0 + tid;
-                bool pass = false;
-                uint32_t nd = 0, p0 = 0;
-                float e = 0.f;
-                if (pos < B) {  // independent loads: one memory round trip per selection pass
-                    if (sel) {
-                        const uint4 se = __ldcg(sel + pos);
-                        e = __uint_as_float(se.x), p0 = se.y, nd = se.z;
-                    } else {
-                        e = __ldcg(est + pos);
-                        p0 = boff[pos];
-                        nd = boff[pos + 1] - p0;
+                bool pass[SP];
+                uint32_t nd[SP], p0[SP], cdl[SP], ccl[SP];
+                float e[SP];
+                uint32_t cd_t = 0, cc_t = 0;  // this thread's totals
+#pragma unroll
+                for (int i = 0; i < SP; ++i) {  // independent loads: one memory round trip per selection pass
+                    const uint32_t pos = pos0 + SP * tid + i;
+                    pass[i] = false, nd[i] = 0, p0[i] = 0, e[i] = 0.f;
+                    if (pos < B) {
+                        if (sel) {
+                            const uint4 se = __ldcg(sel + pos);
+                            e[i] = __uint_as_float(se.x), p0[i] = se.y, nd[i] = se.z;
+                        } else {
+                            e[i] = __ldcg(est + pos);
+                            p0[i] = boff[pos];
+                            nd[i] = boff[pos + 1] - p0[i];
+                        }
+                        pass[i] = !full || !(e[i] < thr);
+                        if (!pass[i]) nd[i] = 0;
                     }
-                    pass = !full || !(e < thr);
-                    if (!pass) nd = 0;
                 }
-                // block-wide inclusive scans of nd and pass
-                uint32_t cd = nd, cc = pass ? 1u : 0u;
+#pragma unroll
+                for (int i = 0; i < SP; ++i) {
+                    cd_t += nd[i], cc_t += pass[i] ? 1u : 0u;
+                    cdl[i] = cd_t, ccl[i] = cc_t;
+                }
+                // block-wide inclusive scans of the documents and of the passing blocks
+                uint32_t cd = cd_t, cc = cc_t;
 #pragma unroll
                 for (int sft = 1; sft < 32; sft <<= 1) {
                     const uint32_t od = __shfl_up_sync(0xffffffffu, cd, sft);
                     const uint32_t oc = __shfl_up_sync(0xffffffffu, cc, sft);
                     if (lane >= (uint32_t)sft) cd += od, cc += oc;
                 }
-                // this block will most likely be in the wave: pull its postings towards L2 ahead of phase 2
-                if (pass && nd && tid < 64 && cd <= cap) {
-                    const char* pp = reinterpret_cast<const char*>(posts + p0);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (size_t)nd * 8 - 8));
+                // these blocks will most likely be in the wave: pull their postings towards L2 ahead of phase 2
+                if (warp == 0) {
+#pragma unroll
+                    for (int i = 0; i < SP; ++i)
+                        if (pass[i] && nd[i] && cd - cd_t + cdl[i] <= cap) {
+                            const char* pp = reinterpret_cast<const char*>(posts + p0[i]);
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (size_t)nd[i] * 8 - 8));
+                        }
                 }
                 if (lane == 31) s_warp_docs[warp] = cd, s_warp_cnt[warp] = cc;
                 if (tid == 0) s_first_rej = 0xffffffffu;
@@ -1450,22 +1469,31 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     if (lane < NW) s_warp_docs[lane] = wd, s_warp_cnt[lane] = wc;
                 }
                 __syncthreads();
-                if (warp > 0) cd += s_warp_docs[warp - 1], cc += s_warp_cnt[warp - 1];
+                // exclusive prefix of this thread (documents / passing blocks before its first position)
+                uint32_t bd = cd - cd_t, bc = cc - cc_t;
+                if (warp > 0) bd += s_warp_docs[warp - 1], bc += s_warp_cnt[warp - 1];
                 // accept while the wave stays within its soft cap; the first passing block is accepted whenever it
                 // fits the buffer; a first passing block larger than the buffer is processed alone, in parts
-                const bool accepted = pass && cd <= (cc == 1 ? a.buf_docs : cap) && cc <= a.cand_cap;
-                if (pass && !accepted) atomicMin(&s_first_rej, pos);
-                if (pass && cc == 1 && !accepted) s_big_nd = nd, s_big_p0 = p0;
+#pragma unroll
+                for (int i = 0; i < SP; ++i) {
+                    const uint32_t cdi = bd + cdl[i], cci = bc + ccl[i];
+                    const bool accepted = pass[i] && cdi <= (cci == 1 ? a.buf_docs : cap) && cci <= a.cand_cap;
+                    if (pass[i] && !accepted) atomicMin(&s_first_rej, pos0 + SP * tid + i);
+                    if (pass[i] && cci == 1 && !accepted) s_big_nd = nd[i], s_big_p0 = p0[i];
+                }
                 __syncthreads();
                 const uint32_t first_rej = s_first_rej;
-                const bool in_wave = pass && pos < first_rej;
-                if (in_wave) {
-                    cand_end[cc - 1] = cd;
-                    cand_est[cc - 1] = e;
-                    cand_p0[cc - 1] = p0;
-                    cand_mx[cc - 1] = 0u;
-                    atomicMax(&s_wave_docs, cd);
-                    atomicMax(&s_wave_cnt, cc);
+#pragma unroll
+                for (int i = 0; i < SP; ++i) {
+                    const uint32_t cdi = bd + cdl[i], cci = bc + ccl[i];
+                    if (pass[i] && pos0 + SP * tid + i < first_rej) {
+                        cand_end[cci - 1] = cdi;
+                        cand_est[cci - 1] = e[i];
+                        cand_p0[cci - 1] = p0[i];
+                        cand_mx[cci - 1] = 0u;
+                        atomicMax(&s_wave_docs, cdi);
+                        atomicMax(&s_wave_cnt, cci);
+                    }
                 }
                 __syncthreads();
                 const uint32_t n_docs = s_wave_docs, n_cand = s_wave_cnt, big_nd = s_big_nd, big_p0 = s_big_p0;
@@ -1493,7 +1521,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     lap(3);
                     continue;
                 }
-                pos0 = first_rej != 0xffffffffu ? first_rej : pos0 + T;
+                pos0 = first_rej != 0xffffffffu ? first_rej : pos0 + SP * T;
                 if (n_cand == 0) continue;
                 first_wave = false;
                 // ---------------- phase 2: gather the postings of all candidate blocks into the wave buffer
