@@ -258,13 +258,13 @@ class Runner:
         self.torch = torch
         self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
         self.flush_rd = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
 
     def flush_l2(self, v):
         """Evict L2: write 512 MB, then read 256 MB so that the write's own dirty lines are written back BEFORE the timed
         region starts (otherwise the first small kernels of the step pay for the harness's write-backs)."""
         self.flush.fill_(v)
         self.flush_sink = self.flush_rd.max()
-        self.stream = torch.cuda.current_stream(dev)
 
     def device_buffers(self, q_off, q_c, q_v, k):
         torch = self.torch
