@@ -257,14 +257,12 @@ class Runner:
         self.a, self.rank, self.local_rank, self.world, self.dev, self.barrier = a, rank, local_rank, world, dev, barrier
         self.torch = torch
         self.flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-        self.flush_rd = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
         self.stream = torch.cuda.current_stream(dev)
 
     def flush_l2(self, v):
-        """Evict L2: write 512 MB, then read 256 MB so that the write's own dirty lines are written back BEFORE the timed
-        region starts (otherwise the first small kernels of the step pay for the harness's write-backs)."""
+        """Evict L2 between timed steps: write 512 MB.  (Reading another 256 MB afterwards, so that no dirty lines are
+        left for the step to write back, was measured: the step's first small kernels got 0.1 ms SLOWER, not faster.)"""
         self.flush.fill_(v)
-        self.flush_sink = self.flush_rd.max()
 
     def device_buffers(self, q_off, q_c, q_v, k):
         torch = self.torch
@@ -501,7 +499,7 @@ def main():
             "config": {"workload": workload_name(a), "queries_per_gpu_per_step": nq, "parallelism": f"replicas x{world}",
                        "index": {"n_postings": a.n_postings, "centroid_fraction": a.centroid_fraction,
                                  "summary_energy": a.summary_energy, "max_fraction": a.max_fraction, "values": "f16"},
-                       "l2": "512 MB buffer written (then 256 MB read, so no dirty lines are left) between timed steps; a step gathers %.1f GB from a %.1f GB image"
+                       "l2": "512 MB buffer written between timed steps; a step gathers %.1f GB from a %.1f GB image"
                              % (stats[-1]["fwd_bytes"] / 1e9, gpu.device_bytes / 1e9)},
             "e2e": {"value": e2e_qps, "unit": "queries/s",
                     "h2d_bytes_per_step": int(q_off.nbytes + q_c.nbytes + q_v.nbytes),
