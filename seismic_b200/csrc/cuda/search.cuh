@@ -748,14 +748,19 @@ template <int D, class Q>
 __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream, const uint64_t (&post)[D],
                                               uint32_t lane8, uint32_t rounds, const Q& q, float (&acc)[D],
                                               uint32_t& bytes, uint32_t lut_s) {
-    const uint8_t* rec[D];
-    uint32_t nch[D], eo[D];  // eo: offset of the lane's exception group in the coming round
+    // All addresses are formed as (stream as 16-byte units) + 32-bit unit index — one IMAD.WIDE each; with 64-bit
+    // record pointers the compiler rematerialised ~30 instructions of pointer arithmetic per chunk under the
+    // 64-register budget.
+    const uint4* s16 = reinterpret_cast<const uint4*>(stream);
+    uint32_t r16[D], t16[D], nch[D], eo[D];  // record start, start of its offset table (16-byte units), chunks,
+                                             // offset of the lane's exception group in the coming round
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        rec[j] = stream + (post[j] >> 16) * RecVB::UNIT_BYTES;
+        r16[j] = (uint32_t)(post[j] >> 16);
         nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
+        t16[j] = r16[j] + nch[j];
         acc[j] = 0.f;
-        eo[j] = lane8 < nch[j] ? __ldg(reinterpret_cast<const uint16_t*>(rec[j] + 16u * nch[j]) + lane8) : 0u;
+        eo[j] = lane8 < nch[j] ? __ldg(reinterpret_cast<const uint16_t*>(s16 + t16[j]) + lane8) : 0u;
         if (lane8 == 0) bytes += 18 * nch[j];
     }
     for (uint32_t r = 0; r < rounds; ++r) {
@@ -766,15 +771,16 @@ __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream
         for (int j = 0; j < D; ++j) {  // every load of the round is issued before the first use; no chunk -> zeros
             fx[j] = make_uint4(0, 0, 0, 0);
             eo_next[j] = 0, w0[j] = 0, w1[j] = 0, w2[j] = 0;
-            const uint8_t* e = rec[j] + 18u * nch[j] + eo[j];
-            al[j] = (uint32_t)reinterpret_cast<uintptr_t>(e) & 3u;
+            const uint4* tail = s16 + t16[j];           // offset table, then (2 * nch bytes further) the exception area
+            const uint32_t off = 2u * nch[j] + eo[j];   // byte offset of the lane's exception group behind `tail`
+            al[j] = off & 3u;                           // `tail` is 16-byte aligned
             if (m < nch[j]) {
-                const uint32_t* ew = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(e) & ~(uintptr_t)3);
-                fx[j] = ld_stream(reinterpret_cast<const uint4*>(rec[j]) + m);
+                const uint32_t* ew = reinterpret_cast<const uint32_t*>(tail) + (off >> 2);
+                fx[j] = ld_stream(s16 + (r16[j] + m));
                 w0[j] = __ldg(ew), w1[j] = __ldg(ew + 1), w2[j] = __ldg(ew + 2);
                 bytes += 1;
             }
-            if (m + 8 < nch[j]) eo_next[j] = __ldg(reinterpret_cast<const uint16_t*>(rec[j] + 16u * nch[j]) + m + 8);
+            if (m + 8 < nch[j]) eo_next[j] = __ldg(reinterpret_cast<const uint16_t*>(tail) + (m + 8));
         }
 #pragma unroll
         for (int j = 0; j < D; ++j) {  // a chunk past the end of a record decodes to (0, +0.0) x 8: adds q * 0 = +-0
