@@ -247,36 +247,31 @@ float doc_score_t(const SgpuIndexView& v, const float* q, uint64_t start, uint32
 constexpr uint32_t VB_UNIT = 16;
 inline uint32_t vb_record_bytes(const SgpuIndexView& v, uint64_t start, uint32_t len) {
     const uint8_t* rec = (const uint8_t*)v.fwd_values + start * VB_UNIT;
-    const uint32_t nch = (len + 7) >> 3;
-    const uint8_t* cum = rec + 16ull * nch;
-    const uint8_t* exc = cum + 2ull * nch;
-    uint32_t bytes = 16 * nch + 2 * nch + nch;
-    for (uint32_t m = 0; m < nch; ++m) {
-        uint16_t eo;
-        std::memcpy(&eo, cum + 2ull * m, 2);
-        bytes += __builtin_popcount(exc[eo]);
+    const uint32_t nch = (len + 7) >> 3, ndir = (nch + 63) >> 6;
+    uint32_t bytes = 16 * ndir + 16 * nch;  // directory, fixed parts; + 8 per wide chunk
+    for (uint32_t t = 0; t < ndir; ++t) {
+        uint64_t mask;
+        std::memcpy(&mask, rec + 16ull * t, 8);
+        bytes += 8 * (uint32_t)__builtin_popcountll(mask);
     }
     return bytes;
 }
 template <int ORDER>
 float doc_score_vbyte(const SgpuIndexView& v, const float* q, uint64_t start, uint32_t len) {
     const uint8_t* rec = (const uint8_t*)v.fwd_values + start * VB_UNIT;
-    const uint32_t nch = (len + 7) >> 3;
-    const uint8_t* cum = rec + 16ull * nch;
-    const uint8_t* exc0 = cum + 2ull * nch;
+    const uint32_t nch = (len + 7) >> 3, ndir = (nch + 63) >> 6;
+    const uint8_t* fixed = rec + 16ull * ndir;
+    const uint8_t* wide = fixed + 16ull * nch;
     const float c24 = 5.9604644775390625e-08f;  // 2^-24
     float p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, seq = 0.f;
+    uint32_t c = 0, n_wide = 0;  // running component (the gaps are one chain over the record), wide chunks so far
     for (uint32_t m = 0; m < nch; ++m) {
-        const uint8_t* fx = rec + 16ull * m;
-        uint16_t eo;
-        std::memcpy(&eo, cum + 2ull * m, 2);
-        const uint8_t* exc = exc0 + eo;
-        const uint32_t ctrl = *exc++;
-        uint32_t c = 0;
+        const uint8_t* fx = fixed + 16ull * m;
+        uint64_t mask;
+        std::memcpy(&mask, rec + 16ull * (m >> 6), 8);
+        const uint8_t* hi = ((mask >> (m & 63)) & 1u) ? wide + 8ull * n_wide++ : nullptr;
         for (uint32_t f = 0; f < 8; ++f) {
-            uint32_t field = fx[f];
-            if (ctrl & (f == 0 ? 0x80u : (1u << (f - 1)))) field |= (uint32_t)(*exc++) << 8;
-            c = f == 0 ? field : c + field;
+            c += (uint32_t)fx[f] | (hi ? (uint32_t)hi[f] << 8 : 0u);
             if (m * 8 + f >= len) continue;  // tail padding: gap 0, code 0
             const float val = (float)fx[8 + f] * c24;
             if (ORDER == ORDER_SEQ) seq = seq + q[c] * val;

@@ -40,9 +40,6 @@ constexpr int HQ_SLOTS = 1 << HQ_LOG2_SLOTS;
 constexpr int HQ_MAX_NNZ = 128;  // HashQuery: queries with more components take the dense kernel
 constexpr int HQ_TRIES = 64;
 constexpr int DENSE_THREADS = 1024;
-#ifndef SGPU_VB_PRMT
-#define SGPU_VB_PRMT 1  // DotVByte: byte-permute decode of the gaps (0: sequential 64-bit shifts)
-#endif
 #ifndef SGPU_DOT2X
 #define SGPU_DOT2X 1
 #endif
@@ -671,18 +668,20 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
     }
 }
 
-// ---- DotVByte records: gap-coded u16 components (1 or 2 bytes per gap) + u8 values --------
+// ---- DotVByte records: gap-coded u16 components (1 or 2 bytes per gap) + u8 values -----------
 // Format: csrc/host/build.cpp (convert_dotvbyte).  The posting's start field counts 16-byte units of the byte stream.
-// Per record: 16 bytes per chunk [8 low bytes of (first component, gap 1..7) | 8 codes], then a u16 per chunk = offset
-// of its exception group, then the exception groups [control byte | the high bytes that exist].  lane8 decodes chunk
-// lane8 of every round: one 128-bit load of its chunk, an unaligned 12-byte window of its exception group (three
-// aligned 32-bit loads; the group's offset was loaded one round ahead, so the loads of a round depend on nothing
-// loaded in that round), byte permutes that line the window up behind the control byte, a 256-entry table of
-// byte-permute selectors that spreads the present high bytes to their fields, four byte-permutes that pair low and
-// high bytes into u16 gaps, a packed prefix sum — and the result is exactly a chunk of the plain layout (4 words of
-// two u16 components, 4 words of two f16 values), fed to the same lookup / multiply-add code.  A code byte c is read
-// as the f16 SUBNORMAL c * 2^-24 (exact), so the f16 -> f32 conversion of the plain layout doubles as the integer ->
-// float conversion; the factor scale * 2^24 is applied once per document (oracle: doc_score_vbyte).
+// Per record: a 16-byte directory entry per super-round of 64 chunks {u64 mask of the WIDE chunks, u32 wide chunks
+// before}, 16 bytes per chunk [8 low bytes of its gaps | 8 codes], 8 bytes per wide chunk [the high bytes of its gaps];
+// the gaps are ONE chain over the record.  lane8 decodes chunk lane8 of every round from TWO loads — its 16 fixed bytes
+// and, if its mask bit is set, its 8 high bytes (rank by popcount) — which is what the uncompressed layout issues too:
+// with the previous layout (control bit per component, exception groups behind a u16 offset table: 5 loads per chunk)
+// the decode arithmetic measured as free and the three extra loads as the whole 24 % gap to f16
+// (profiles/r2_dotvbyte_loads_experiment.log).  Four byte-permutes pair low and high bytes into u16 gaps, a packed
+// prefix sum ((a, b) * 0x10001 = (a, a + b)) chains them inside the chunk, an 8-lane shuffle scan of the chunk totals
+// plus the carry of the earlier rounds gives the chunk's first component — and the result is exactly a chunk of the plain
+// layout (4 words of two u16 components, 4 words of two f16 values), fed to the same lookup / multiply-add code.  A code
+// byte c is read as the f16 SUBNORMAL c * 2^-24 (exact), so the f16 -> f32 conversion of the plain layout doubles as the
+// integer -> float conversion; the factor scale * 2^24 is applied once per document (oracle: doc_score_vbyte).
 struct RecVB {
     static constexpr bool VBYTE = true;
     static constexpr bool PLAIN_F16 = false;
@@ -699,93 +698,100 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
-// Table entry for control byte t (bit 7: the first component has a high byte, bit f-1: gap f has one).  The present
-// high bytes are consecutive behind the control byte, first component first.  x / y = byte-permute selectors for the
-// high bytes of fields 0..3 / 4..7 out of the 8 bytes that follow the control byte, z / w = masks clearing the absent.
-__device__ __forceinline__ uint4 vb_lut_entry(uint32_t t) {
-    uint32_t sel[2] = {0, 0}, msk[2] = {0, 0}, pos = 0;
-#pragma unroll
-    for (uint32_t f = 0; f < 8; ++f) {
-        const bool present = f == 0 ? (t >> 7) & 1u : (t >> (f - 1)) & 1u;
-        if (present) {
-            sel[f >> 2] |= pos << (4 * (f & 3));
-            msk[f >> 2] |= 0xffu << (8 * (f & 3));
-            ++pos;
-        }
-    }
-    return make_uint4(sel[0], sel[1], msk[0], msk[1]);
-}
-
-// one chunk of a DotVByte record -> the plain layout's (component words, value words).  `fx` = its 16 fixed bytes,
-// (w0, w1, w2) = the aligned 12-byte window that holds its exception group from byte `a` on.  All-zero inputs (a lane
-// without a chunk in this round) decode to all-zero outputs: no branch around the decode is needed.
-__device__ __forceinline__ void vb_decode(const uint4 fx, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t a, uint32_t lut_s,
-                                          uint4& c, uint4& v, uint32_t& bytes) {
-    const uint32_t ctrl = prmt(w0, 0u, 0x4440u + a);       // byte a of the window, zero-extended
-    const uint32_t sel = 0x4321u + a * 0x1111u;            // the four bytes behind it ...
-    const uint32_t X0 = prmt(w0, w1, sel), X1 = prmt(w1, w2, sel);  // ... and the four after those
-    uint4 lu;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(lu.x), "=r"(lu.y), "=r"(lu.z), "=r"(lu.w) : "r"(lut_s + ctrl * 16));
-    const uint32_t H0 = prmt(X0, X1, lu.x) & lu.z, H1 = prmt(X0, X1, lu.y) & lu.w;
-    // (low byte, high byte) pairs -> u16 fields, two per word
-    const uint32_t P01 = prmt(fx.x, H0, 0x5140), P23 = prmt(fx.x, H0, 0x7362);
-    const uint32_t P45 = prmt(fx.y, H1, 0x5140), P67 = prmt(fx.y, H1, 0x7362);
-    // packed prefix sum: (a, b) * 0x10001 = (a, a + b); components stay below 2^16, so no carry crosses the halves
-    c.x = P01 * 0x10001u;
-    c.y = (P23 + (c.x >> 16)) * 0x10001u;
-    c.z = (P45 + (c.y >> 16)) * 0x10001u;
-    c.w = (P67 + (c.z >> 16)) * 0x10001u;
-    // codes -> f16 subnormals (code * 2^-24), two per word
-    v.x = prmt(fx.z, 0u, 0x4140);
-    v.y = prmt(fx.z, 0u, 0x4342);
-    v.z = prmt(fx.w, 0u, 0x4140);
-    v.w = prmt(fx.w, 0u, 0x4342);
-    bytes += __popc(ctrl);
-}
-
 template <int D, class Q>
 __device__ __forceinline__ void score_docs_vb(const uint8_t* __restrict__ stream, const uint64_t (&post)[D],
                                               uint32_t lane8, uint32_t rounds, const Q& q, float (&acc)[D],
-                                              uint32_t& bytes, uint32_t lut_s) {
-    // All addresses are formed as (stream as 16-byte units) + 32-bit unit index — one IMAD.WIDE each; with 64-bit
-    // record pointers the compiler rematerialised ~30 instructions of pointer arithmetic per chunk under the
-    // 64-register budget.
+                                              uint32_t& bytes) {
+    // all addresses are (stream as 16-byte units) + 32-bit unit index: one IMAD.WIDE each
     const uint4* s16 = reinterpret_cast<const uint4*>(stream);
-    uint32_t r16[D], t16[D], nch[D], eo[D];  // record start, start of its offset table (16-byte units), chunks,
-                                             // offset of the lane's exception group in the coming round
+    uint32_t r16[D], nch[D], f16[D], w16[D];  // record start, chunks, first fixed part, wide area (16-byte units)
+    uint32_t mlo[D], mhi[D], wbef[D], carry[D];  // current directory entry; components of the earlier rounds summed
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         r16[j] = (uint32_t)(post[j] >> 16);
         nch[j] = ((uint32_t)(post[j] & 0xffffu) + 7) >> 3;
-        t16[j] = r16[j] + nch[j];
+        const uint32_t ndir = (nch[j] + 63) >> 6;
+        f16[j] = r16[j] + ndir;
+        w16[j] = f16[j] + nch[j];
+        mlo[j] = mhi[j] = wbef[j] = carry[j] = 0;
         acc[j] = 0.f;
-        eo[j] = lane8 < nch[j] ? __ldg(reinterpret_cast<const uint16_t*>(s16 + t16[j]) + lane8) : 0u;
-        if (lane8 == 0) bytes += 18 * nch[j];
+        if (lane8 == 0) bytes += 16 * (ndir + nch[j]);
     }
-    for (uint32_t r = 0; r < rounds; ++r) {
+    for (uint32_t r = 0; r < rounds; ++r) {  // `rounds` and therefore r are warp-uniform
         const uint32_t m = lane8 + 8 * r;
-        uint4 c[D], v[D], fx[D];
-        uint32_t eo_next[D], w0[D], w1[D], w2[D], al[D];
+        if ((r & 7) == 0) {  // a new super-round: its directory entry (the 8 lanes of a group read the same 16 bytes)
 #pragma unroll
-        for (int j = 0; j < D; ++j) {  // every load of the round is issued before the first use; no chunk -> zeros
-            fx[j] = make_uint4(0, 0, 0, 0);
-            eo_next[j] = 0, w0[j] = 0, w1[j] = 0, w2[j] = 0;
-            const uint4* tail = s16 + t16[j];           // offset table, then (2 * nch bytes further) the exception area
-            const uint32_t off = 2u * nch[j] + eo[j];   // byte offset of the lane's exception group behind `tail`
-            al[j] = off & 3u;                           // `tail` is 16-byte aligned
-            if (m < nch[j]) {
-                const uint32_t* ew = reinterpret_cast<const uint32_t*>(tail) + (off >> 2);
-                fx[j] = ld_stream(s16 + (r16[j] + m));
-                w0[j] = __ldg(ew), w1[j] = __ldg(ew + 1), w2[j] = __ldg(ew + 2);
-                bytes += 1;
+            for (int j = 0; j < D; ++j) {
+                uint4 de = make_uint4(0, 0, 0, 0);
+                if (8 * r < nch[j]) de = ld_stream(s16 + (r16[j] + (r >> 3)));
+                mlo[j] = de.x, mhi[j] = de.y, wbef[j] = de.z;
             }
-            if (m + 8 < nch[j]) eo_next[j] = __ldg(reinterpret_cast<const uint16_t*>(tail) + (m + 8));
+        }
+        const uint32_t b = lane8 + 8 * (r & 7);  // bit of chunk m in the mask of its super-round
+        uint4 c[D], v[D], fx[D];
+        uint2 hi[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {  // both loads of every chunk of the round are issued before the first use
+            uint32_t w, below;
+            if ((r & 4) == 0) {  // b < 32 (uniform)
+                w = mlo[j];
+                below = __popc(mlo[j] & ((1u << b) - 1u));
+            } else {
+                w = mhi[j];
+                below = __popc(mlo[j]) + __popc(mhi[j] & ((1u << (b & 31)) - 1u));
+            }
+            fx[j] = make_uint4(0, 0, 0, 0);
+            hi[j] = make_uint2(0, 0);
+            if (m < nch[j]) fx[j] = ld_stream(s16 + (f16[j] + m));
+            if ((w >> (b & 31)) & 1u) {  // mask bits exist only for chunks of the record
+                hi[j] = __ldg(reinterpret_cast<const uint2*>(s16 + w16[j]) + (wbef[j] + below));
+                bytes += 8;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < D; ++j) {  // a chunk past the end of a record decodes to (0, +0.0) x 8: adds q * 0 = +-0
-            vb_decode(fx[j], w0[j], w1[j], w2[j], al[j], lut_s, c[j], v[j], bytes);
-            eo[j] = eo_next[j];
+        for (int j = 0; j < D; ++j) {  // a chunk past the end of a record is all zero: (last component, +0.0) x 8
+            // (low byte, high byte) pairs -> u16 gaps, two per word; packed prefix sum inside the chunk (the gaps of
+            // a record sum to less than 2^16, so no carry crosses the halves)
+            c[j].x = prmt(fx[j].x, hi[j].x, 0x5140) * 0x10001u;
+            c[j].y = (prmt(fx[j].x, hi[j].x, 0x7362) + (c[j].x >> 16)) * 0x10001u;
+            c[j].z = (prmt(fx[j].y, hi[j].y, 0x5140) + (c[j].y >> 16)) * 0x10001u;
+            c[j].w = (prmt(fx[j].y, hi[j].y, 0x7362) + (c[j].z >> 16)) * 0x10001u;
+            // codes -> f16 subnormals (code * 2^-24), two per word
+            v[j].x = prmt(fx[j].z, 0u, 0x4140);
+            v[j].y = prmt(fx[j].z, 0u, 0x4342);
+            v[j].z = prmt(fx[j].w, 0u, 0x4140);
+            v[j].w = prmt(fx[j].w, 0u, 0x4342);
+        }
+        // first component of every chunk = components of the earlier rounds + of the lower lanes of this round: an
+        // 8-lane inclusive scan of the chunk totals.  Totals and their sums stay below 2^16, so the two documents of a
+        // group are scanned as the halves of one register.
+        if constexpr (D == 2) {
+            const uint32_t tot = prmt(c[0].w, c[1].w, 0x7632);  // (total of document 0, total of document 1)
+            uint32_t incl = tot;
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft, 8);
+                if (lane8 >= (uint32_t)sft) incl += up;
+            }
+            const uint32_t base = carry[0] + incl - tot;
+            carry[0] += __shfl_sync(0xffffffffu, incl, 7, 8);
+            const uint32_t b0 = prmt(base, 0u, 0x1010), b1 = prmt(base, 0u, 0x3232);  // each half copied into both halves
+            c[0].x += b0, c[0].y += b0, c[0].z += b0, c[0].w += b0;
+            c[1].x += b1, c[1].y += b1, c[1].z += b1, c[1].w += b1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const uint32_t tot = c[j].w >> 16;
+                uint32_t incl = tot;
+#pragma unroll
+                for (int sft = 1; sft < 8; sft <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft, 8);
+                    if (lane8 >= (uint32_t)sft) incl += up;
+                }
+                const uint32_t base2 = (carry[j] + incl - tot) * 0x10001u;
+                carry[j] += __shfl_sync(0xffffffffu, incl, 7, 8);
+                c[j].x += base2, c[j].y += base2, c[j].z += base2, c[j].w += base2;
+            }
         }
         if constexpr (D == 2 && Q::HAS_DOT8) {
             q.dot2x(acc[0], acc[1], c, v);
@@ -1111,9 +1117,6 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     }
 
     __shared__ uint32_t s_q;
-    __shared__ uint4 s_vb_lut[is_vbyte<R>::value ? 256 : 1];  // DotVByte decode (vb_lut_entry); visible after the first barrier of the loop
-    if constexpr (is_vbyte<R>::value)
-        for (uint32_t i = threadIdx.x; i < 256; i += T) s_vb_lut[i] = vb_lut_entry(i);
     __shared__ uint32_t s_warp_docs[32], s_warp_cnt[32];
     __shared__ uint32_t s_first_rej, s_wave_docs, s_wave_cnt, s_big_nd, s_big_p0, s_snap_n;
     __shared__ float s_theta;
@@ -1127,10 +1130,10 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
     const uint32_t lane8 = tid & 7, grp = tid >> 3;
     const uint32_t k = a.k;
 
-    // bytes of a posting's record (DotVByte: without the exception area's exact size, ~4 per chunk)
+    // bytes of a posting's record (DotVByte: as if every chunk were wide)
     auto rec_bytes = [&](uint64_t pst) -> uint32_t {
         const uint32_t nch = ((uint32_t)(pst & 0xffffu) + 7) >> 3;
-        if constexpr (is_vbyte<R>::value) return 23 * nch;
+        if constexpr (is_vbyte<R>::value) return 16 + 24 * nch;
         else return nch * R::CHUNK_BYTES;
     };
     H heap;  // live in warp 0 only
@@ -1293,8 +1296,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
             const uint32_t rounds = (__reduce_max_sync(0xffffffffu, mx) + 63) >> 6;
             float acc[D];
             if constexpr (is_vbyte<R>::value)
-                score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, acc, st_units,
-                                 (uint32_t)__cvta_generic_to_shared(s_vb_lut));
+                score_docs_vb<D>(reinterpret_cast<const uint8_t*>(a.ix.fwd), post, lane8, rounds, query, acc, st_units);
             else
                 score_docs<D, R>(a.ix.fwd, post, lane8, rounds, query, a.value_scale, acc);
 #pragma unroll

@@ -723,22 +723,25 @@ void fill_view(const ShostIndex& idx, SgpuIndexView* v) {
 // forward index to `PackedSparseDataset<DotVByteFixedU8Encoder>` (src/pylib/dotvbyte.rs:195-213), re-packing the
 // postings to the packed storage's ranges (src/inverted_index.rs:237-275).  The byte format of that encoder lives
 // in the absent `vectorium` crate, so this is OUR documented format (not byte-compatible): a variable-byte code of the
-// component gaps (1 or 2 bytes per gap, stream-vbyte style control bits) + u8 fixed-point values, laid out so that a
-// GPU lane decodes one chunk of 8 components with wide aligned loads and byte permutes.
+// component gaps (1 or 2 bytes per gap) + u8 fixed-point values, laid out so that a GPU lane decodes one chunk of 8
+// components from TWO aligned loads.  (Measured on the previous layout — one control bit per component, per-chunk
+// exception groups behind a u16 offset table, five loads per chunk: the decode arithmetic was free, the three extra
+// loads were the whole gap to the uncompressed index.  Hence the control bit per CHUNK: all eight gaps of a chunk take
+// one byte, or all take two.)
 //
 //   value    u8 code, value = code * scale, scale = (largest f16 value of the collection) / 255   (FixedU8)
-//   record   16-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)):
-//     fixed  16 bytes per chunk: lo[8] = LOW bytes of (first component, gap 1, ..., gap 7), then val[8] = the 8 codes
-//            (tail of the last chunk: gap 0, code 0)
-//     cum    u16 per chunk: offset of the chunk's exception group inside the record's exception area
-//     exc    one group per chunk: the control byte (bit 7 = the first component has a HIGH byte, bit j-1 = gap j has
-//            one, j = 1..7), then the high bytes that exist — first component, then gaps 1..7
+//   gaps     gap_i = component_i - component_{i-1} (gap_0 = component_0): ONE chain over the whole record, < 2^16 each
+//   record   16-byte aligned; components in chunks of 8 (nch = ceil(nnz/8)), chunks in super-rounds of 64:
+//     dir    16 bytes per super-round: u64 mask (bit b = chunk 64 t + b is WIDE: one of its gaps is >= 256),
+//            u32 number of wide chunks in the earlier super-rounds, u32 zero
+//     fixed  16 bytes per chunk: lo[8] = LOW bytes of its gaps, then val[8] = its codes (tail of the last chunk: gap 0,
+//            code 0)
+//     wide   8 bytes per WIDE chunk, in chunk order: the HIGH bytes of its gaps
 //     zero padding to a multiple of 16 bytes
 //   fwd_offsets[i]  byte offset of record i;  fwd_nnz[i] number of components;  postings = (offset/16 << 16) | nnz
-// Every chunk is self-contained given its u16 offset (absolute first component), so the 8 lanes of a GPU group decode
-// 8 chunks in parallel, and the loads of a chunk (its 16 fixed bytes, its exception group) do not depend on any
-// other chunk's data.  (A record has at most 8192 chunks, hence at most 2 * 8192 + 255 exception-area bytes — the
-// gaps of one vector sum to less than 2^16, so at most 255 of them need a high byte: the offsets fit u16.)
+// A GPU lane handles chunk m = lane + 8 r in round r: its wide bit and the rank of its wide entry come from the
+// directory entry (loaded once per 8 rounds) by popcount, its loads are the 16 fixed bytes and (if wide) the 8 high
+// bytes; the chunk's first component is the running total of the record so far, an 8-lane shuffle scan per round.
 namespace shost {
 
 int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
@@ -754,21 +757,24 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     float mx = 0.f;
     for (uint64_t i = 0; i < in.nnz; ++i) mx = std::max(mx, f16_bits_to_f32(vals[i]));
     const float scale = mx > 0.f ? mx / 255.f : 1.f;
-    // field f (0..7) of chunk m: the first component (f = 0) or gap f
-    auto field = [&](uint64_t s, uint64_t n, uint32_t m, uint32_t f) -> uint32_t {
-        const uint64_t i = (uint64_t)m * 8 + f;
+    // gap i of a record: one chain over the whole record
+    auto gap = [&](uint64_t s, uint64_t n, uint64_t i) -> uint32_t {
         if (i >= n) return 0u;
-        return f == 0 ? (uint32_t)comps[s + i] : (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1];
+        return i == 0 ? (uint32_t)comps[s] : (uint32_t)comps[s + i] - (uint32_t)comps[s + i - 1];
+    };
+    auto chunk_wide = [&](uint64_t s, uint64_t n, uint32_t m) -> bool {
+        for (uint32_t f = 0; f < 8; ++f)
+            if (gap(s, n, (uint64_t)m * 8 + f) >= 256) return true;
+        return false;
     };
     // pass 1: record sizes
     std::vector<uint64_t> boff(N + 1, 0);
     parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t d = b; d < e; ++d) {
             const uint64_t s = off[d], n = off[d + 1] - s;
-            const uint32_t nch = (uint32_t)((n + 7) >> 3);
-            uint64_t bytes = 16ull * nch + 2ull * nch + nch;  // fixed parts, offsets, control bytes
-            for (uint32_t m = 0; m < nch; ++m)
-                for (uint32_t f = 0; f < 8; ++f) bytes += field(s, n, m, f) >= 256 ? 1 : 0;
+            const uint32_t nch = (uint32_t)((n + 7) >> 3), ndir = (nch + 63) >> 6;
+            uint64_t bytes = 16ull * ndir + 16ull * nch;  // directory, fixed parts
+            for (uint32_t m = 0; m < nch; ++m) bytes += chunk_wide(s, n, m) ? 8 : 0;
             boff[d + 1] = (bytes + 15) & ~15ull;
         }
     });
@@ -789,31 +795,32 @@ int convert_dotvbyte(const ShostIndex& in, ShostIndex** out) {
     parallel_for(N, 8192, T, [&](uint64_t b, uint64_t e, unsigned) {
         for (uint64_t d = b; d < e; ++d) {
             const uint64_t s = off[d], n = off[d + 1] - s;
-            const uint32_t nch = (uint32_t)((n + 7) >> 3);
+            const uint32_t nch = (uint32_t)((n + 7) >> 3), ndir = (nch + 63) >> 6;
             nnzs[d] = (uint16_t)n;
             uint8_t* rec = stream + boff[d];
             std::memset(rec, 0, boff[d + 1] - boff[d]);
-            uint8_t* cum = rec + 16ull * nch;
-            uint8_t* exc0 = cum + 2ull * nch;
-            uint8_t* exc = exc0;
+            uint8_t* fixed = rec + 16ull * ndir;
+            uint8_t* wide = fixed + 16ull * nch;
+            uint32_t n_wide = 0;
             for (uint32_t m = 0; m < nch; ++m) {
-                const uint16_t eo = (uint16_t)(exc - exc0);
-                std::memcpy(cum + 2ull * m, &eo, 2);
-                uint8_t* fx = rec + 16ull * m;
-                uint8_t* ctrl = exc++;
-                uint8_t c = 0;
+                if ((m & 63) == 0) std::memcpy(rec + 16ull * (m >> 6) + 8, &n_wide, 4);  // wide chunks before this super-round
+                uint8_t* fx = fixed + 16ull * m;
+                const bool w = chunk_wide(s, n, m);
                 for (uint32_t f = 0; f < 8; ++f) {
                     const uint64_t i = (uint64_t)m * 8 + f;
                     const float r = i < n ? std::nearbyint(f16_bits_to_f32(vals[s + i]) / scale) : 0.f;
                     fx[8 + f] = (uint8_t)std::min(255.f, std::max(0.f, r));
-                    const uint32_t v = field(s, n, m, f);
-                    fx[f] = (uint8_t)(v & 0xff);
-                    if (v >= 256) {
-                        *exc++ = (uint8_t)(v >> 8);
-                        c |= (uint8_t)(f == 0 ? 0x80u : (1u << (f - 1)));
-                    }
+                    const uint32_t g = gap(s, n, i);
+                    fx[f] = (uint8_t)(g & 0xff);
+                    if (w) wide[8ull * n_wide + f] = (uint8_t)(g >> 8);
                 }
-                *ctrl = c;
+                if (w) {
+                    uint64_t mask;
+                    std::memcpy(&mask, rec + 16ull * (m >> 6), 8);
+                    mask |= 1ull << (m & 63);
+                    std::memcpy(rec + 16ull * (m >> 6), &mask, 8);
+                    ++n_wide;
+                }
             }
         }
     });

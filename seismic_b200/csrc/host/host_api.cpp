@@ -141,21 +141,18 @@ int shost_index_get_doc(const ShostIndex* idx, uint64_t id, uint32_t* comps, flo
     if (idx->value_kind == SGPU_VAL_DOTVBYTE) {  // decode of the packed record (format: build.cpp, convert_dotvbyte)
         const uint64_t* boff = idx->sec[SEC_FWD_OFFSETS].as<uint64_t>();
         const uint8_t* rec = idx->sec[SEC_FWD_VALUES].as<uint8_t>() + boff[id];
-        const uint32_t n = idx->sec[SEC_FWD_NNZ].as<uint16_t>()[id], nch = (n + 7) >> 3;
-        const uint8_t* cum = rec + 16ull * nch;
-        const uint8_t* exc0 = cum + 2ull * nch;
+        const uint32_t n = idx->sec[SEC_FWD_NNZ].as<uint16_t>()[id], nch = (n + 7) >> 3, ndir = (nch + 63) >> 6;
+        const uint8_t* fixed = rec + 16ull * ndir;
+        const uint8_t* wide = fixed + 16ull * nch;
         *nnz = n;
-        uint32_t c = 0;
+        uint32_t c = 0, n_wide = 0;
         for (uint32_t m = 0; m < nch; ++m) {
-            const uint8_t* fx = rec + 16ull * m;
-            uint16_t eo;
-            std::memcpy(&eo, cum + 2ull * m, 2);
-            const uint8_t* exc = exc0 + eo;
-            const uint32_t ctrl = *exc++;
+            const uint8_t* fx = fixed + 16ull * m;
+            uint64_t mask;
+            std::memcpy(&mask, rec + 16ull * (m >> 6), 8);
+            const uint8_t* hi = ((mask >> (m & 63)) & 1u) ? wide + 8ull * n_wide++ : nullptr;
             for (uint32_t f = 0; f < 8; ++f) {
-                uint32_t field = fx[f];
-                if (ctrl & (f == 0 ? 0x80u : (1u << (f - 1)))) field |= (uint32_t)(*exc++) << 8;
-                c = f == 0 ? field : c + field;
+                c += (uint32_t)fx[f] | (hi ? (uint32_t)hi[f] << 8 : 0u);
                 const uint32_t i = m * 8 + f;
                 if (i < n && i < cap) comps[i] = c, values[i] = (float)fx[8 + f] * idx->value_scale;
             }

@@ -144,10 +144,11 @@ class PyIndex:
 
 def decode_dotvbyte(host):
     """Independent decoder of the DotVByte forward index (format: seismic_b200/csrc/host/build.cpp, convert_dotvbyte;
-    the reference's own byte format lives in vectorium).  Per document, 16-byte aligned: [16 bytes per chunk of 8
-    components: 8 low bytes of (first component, gap 1..7) | 8 u8 codes][u16 per chunk: offset of its exception group]
-    [exception groups: control byte, then the high bytes that exist, in order].  Control byte: bit 7 = first component
-    has a high byte, bit j-1 = gap j has one.  Returns CSR (offsets, components, values = code * scale, codes)."""
+    the reference's own byte format lives in vectorium).  Per document, 16-byte aligned, nch = ceil(nnz / 8) chunks:
+    [16 bytes per super-round of 64 chunks: u64 mask of the WIDE chunks, u32 wide chunks before, u32 zero]
+    [16 bytes per chunk: 8 low bytes of its gaps | 8 u8 codes][8 bytes per wide chunk: the high bytes of its gaps].
+    The gaps are one chain over the record (gap 0 = first component).  Returns CSR (offsets, components,
+    values = code * scale, codes)."""
     from seismic_b200 import _native as N
     v = host.view
     n = host.len
@@ -161,28 +162,31 @@ def decode_dotvbyte(host):
         rec = stream[int(fo[d]):int(fo[d + 1])]
         ln = int(nnzs[d])
         nch = (ln + 7) // 8
-        cum = rec[16 * nch: 18 * nch].view(np.uint16)
-        exc = rec[18 * nch:]
-        running = 0
+        ndir = (nch + 63) // 64
+        fixed = rec[16 * ndir: 16 * ndir + 16 * nch]
+        wide = rec[16 * ndir + 16 * nch:]
+        c, n_wide = 0, 0
         for m in range(nch):
-            fx = rec[16 * m: 16 * m + 16]
-            e = int(cum[m])
-            assert e == running, "exception groups are laid end to end"
-            ctrl = int(exc[e]); e += 1
-            c = 0
+            entry = rec[16 * (m // 64): 16 * (m // 64) + 16]
+            mask = int(entry[:8].view(np.uint64)[0])
+            if m % 64 == 0:
+                assert int(entry[8:12].view(np.uint32)[0]) == n_wide and not entry[12:].any()
+                assert mask >> min(64, nch - m) == 0, "no mask bits beyond the last chunk"
+            fx = fixed[16 * m: 16 * m + 16]
+            is_wide = (mask >> (m % 64)) & 1
+            hi = wide[8 * n_wide: 8 * n_wide + 8] if is_wide else np.zeros(8, np.uint8)
+            n_wide += is_wide
+            gaps = [int(fx[f]) | (int(hi[f]) << 8) for f in range(8)]
+            assert bool(is_wide) == (max(gaps) >= 256), "a chunk is wide iff one of its gaps needs two bytes"
             for f in range(8):
-                field = int(fx[f])
-                if ctrl & (0x80 if f == 0 else (1 << (f - 1))):
-                    field |= int(exc[e]) << 8
-                    e += 1
-                c = field if f == 0 else c + field
+                c += gaps[f]
                 if m * 8 + f < ln:
                     comps.append(c)
                     codes.append(int(fx[8 + f]))
                     vals.append(np.float32(np.float32(fx[8 + f]) * scale))
                 else:
-                    assert field == 0 and fx[8 + f] == 0
-            running = e
-        assert not rec[18 * nch + running:].any(), "padding must be zero"
+                    assert gaps[f] == 0 and fx[8 + f] == 0
+        assert not wide[8 * n_wide:].any(), "padding must be zero"
+        assert len(rec) == (16 * ndir + 16 * nch + 8 * n_wide + 15) // 16 * 16
         off.append(len(comps))
     return np.array(off, np.uint64), np.array(comps, np.uint32), np.array(vals, np.float32), np.array(codes, np.uint8)
