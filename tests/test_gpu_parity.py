@@ -188,8 +188,8 @@ def test_parity_dotvbyte(oracle_mod, synth_pruned, k, cut, hf, srt):
 
 
 def test_dotvbyte_wide_documents(oracle_mod):
-    """Documents with hundreds of components (many chunks: the prefix popcount spans several control words) and
-    gaps that straddle every byte alignment."""
+    """Documents with up to 700 components (two super-rounds of 64 chunks: the wide-chunk rank spans directory entries
+    and both mask words), narrow and wide chunks mixed, an empty document, and queries of > 255 components."""
     rng = np.random.default_rng(5)
     comps, vals = [], []
     for i in range(600):
