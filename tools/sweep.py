@@ -33,14 +33,8 @@ q = Dataset.synth_queries(cfg, a.queries)
 gpu = GpuIndex(index, 0)
 nr = min(a.recall_queries, a.queries)
 r_off = q.offsets[: nr + 1]
-if a.comp_bits == 16:
-    ex = gpu.exact_search(r_off, q.comps[: int(r_off[-1])], q.values[: int(r_off[-1])], a.k)
-    print("exact ms", gpu.last_stats, flush=True)
-else:  # no GPU exact kernel for u32 components: CPU brute force on the sample
-    import oracle
-    t = time.time()
-    ex = oracle.exact_search(index.view, r_off, q.comps[: int(r_off[-1])], q.values[: int(r_off[-1])], a.k)
-    print("exact (cpu) s", round(time.time() - t, 1), flush=True)
+ex = gpu.exact_search(r_off, q.comps[: int(r_off[-1])], q.values[: int(r_off[-1])], a.k)  # every plain layout, u32 included
+print("exact ms", gpu.last_stats, flush=True)
 rows = []
 for cut in [int(x) for x in a.cuts.split(',')]:
     for hf in [float(x) for x in a.hfs.split(',')]:
@@ -54,10 +48,13 @@ for cut in [int(x) for x in a.cuts.split(',')]:
             rec = recall_at_k(ex[0], ex[2], ids[:nr], cnt[:nr])
             if a.comp_bits == 32 and cut == int(a.cuts.split(',')[0]) and hf == float(a.hfs.split(',')[0]):
                 import oracle
-                n = min(2000, a.queries)
+                n = a.queries  # whole batch: parity and the algorithmic bytes of the roofline
                 o = q.offsets[: n + 1]
                 ref = oracle.batch_search(index.view, o, q.comps[: int(o[-1])], q.values[: int(o[-1])], a.k, cut, hf,
                                           first_sorted=srt, n_threads=0)
+                alg = ref[3]["bytes_postings"] + ref[3]["bytes_forward"] + ref[3]["bytes_query_out"]
+                print(json.dumps({"k_search_algorithmic_bytes_first_%d" % n: alg,
+                                  "docs_scored_reference_first_%d" % n: ref[3]["docs_scored"]}), flush=True)
                 print(json.dumps({"lv_parity_mismatch_first_%d" % n: int(((ids[:n] != ref[0]).any(axis=1) | (cnt[:n] != ref[2])).sum()),
                                   "scores_equal": bool(np.array_equal(sc[:n], ref[1])),
                                   "cpu_all_threads_qps": round(n / ref[3]["seconds"]),
