@@ -91,28 +91,13 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
                  : "l"(p));
     return r;
 }
-// The u16 / f16 record is stored ROUND-PLANAR: the (up to) 8 chunks of a round keep their 16 bytes of components
-// together, followed by their 16 bytes of values — [c0 .. c7 | v0 .. v7], a tail round of T chunks is [c0 .. cT-1 |
-// v0 .. vT-1].  The 8 lanes of a group then read 128 contiguous bytes per load instruction (4 sectors, each used in
-// full) instead of the first or second half of 8 different sectors: half the sector lookups, no reliance on L1 hits for
-// the second halves.  (SGPU_REC16_PLANAR = 0: chunk-interleaved [c | v] with chunks 4..7 of a round swapped.)
-// chunk m of a record of nch chunks; `p` = record + 32 * m
-__device__ __forceinline__ void ld_chunk(const char* p, uint32_t m, uint32_t nch, uint4& c, uint4& v) {
-#if SGPU_REC16_PLANAR
-    const uint32_t g = m & 7u, t = min(8u, nch - (m & ~7u));
-    const uint4* pc = reinterpret_cast<const uint4*>(p - 16u * g);  // round base + 16 * g
-    c = ld_stream(pc);
-    v = ld_stream(pc + t);
-#else
-    const uint32_t sw = (m >> 2) & 1u;
-    c = ld_stream(reinterpret_cast<const uint4*>(p) + sw);
-    v = ld_stream(reinterpret_cast<const uint4*>(p) + (sw ^ 1u));
-#endif
-}
-// the chunk-interleaved layouts of the other 32-byte encodings (bf16, fixedu16)
-__device__ __forceinline__ void ld_chunk_cv(const uint4* p, uint4& c, uint4& v) {
-    c = ld_stream(p);
-    v = ld_stream(p + 1);
+// One 32-byte chunk of the u16 / f16 layout (8 components + 8 values) with two 128-bit loads.  Chunks 4..7 of every
+// round of 8 are stored [values | components] instead of [components | values] (`sw` = bit 2 of the chunk index): when
+// the 8 lanes of a group read the same half of their chunks from SHARED memory (TMA-staged rounds) the 16-byte pieces
+// then fall into 8 distinct bank quads; from global memory the order is irrelevant.
+__device__ __forceinline__ void ld_chunk(const uint4* p, uint32_t sw, uint4& c, uint4& v) {
+    c = ld_stream(p + sw);
+    v = ld_stream(p + (sw ^ 1u));
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -469,8 +454,8 @@ struct Rec16 {  // u16 components: chunk = [8 x u16 | 8 x f16] = 32 bytes = 2 x 
     static constexpr int CHUNK_BYTES = 32;
     static constexpr int UNIT_BYTES = 32;  // unit of the posting's start field
     struct Chunk { uint4 c, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t m, uint32_t nch) {
-        ld_chunk(p, m, nch, k.c, k.v);
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t m) {
+        ld_chunk(reinterpret_cast<const uint4*>(p), (m >> 2) & 1u, k.c, k.v);
     }
     template <class Q>
     static __device__ __forceinline__ float dot(float acc, const Chunk& k, const Q& q, float) {
@@ -489,7 +474,7 @@ struct Rec32 {  // u32 components (large vocabulary): chunk = [8 x u32 | 8 x f16
     static constexpr int CHUNK_BYTES = 48;
     static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c0, c1, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t, uint32_t) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         const uint4* p4 = reinterpret_cast<const uint4*>(p);
         k.c0 = ld_stream(p4);
         k.c1 = ld_stream(p4 + 1);
@@ -521,8 +506,8 @@ struct Rec16V2 {
     static constexpr int CHUNK_BYTES = 32;
     static constexpr int UNIT_BYTES = 32;
     struct Chunk { uint4 c, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t, uint32_t) {
-        ld_chunk_cv(reinterpret_cast<const uint4*>(p), k.c, k.v);
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
+        ld_chunk(reinterpret_cast<const uint4*>(p), 0u, k.c, k.v);
     }
     static __device__ __forceinline__ float val(uint32_t vw, bool hi, float scale) {
         if constexpr (KIND == 1) return __uint_as_float(hi ? (vw & 0xffff0000u) : (vw << 16));
@@ -544,7 +529,7 @@ struct Rec16F32 {  // chunk = [8 x u16 | 8 x f32] = 48 bytes, unit 16 bytes
     static constexpr int CHUNK_BYTES = 48;
     static constexpr int UNIT_BYTES = 16;
     struct Chunk { uint4 c, v0, v1; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t, uint32_t) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         const uint4* p4 = reinterpret_cast<const uint4*>(p);
         k.c = ld_stream(p4);
         k.v0 = ld_stream(p4 + 1);
@@ -567,7 +552,7 @@ struct Rec16U8 {  // chunk = [8 x u16 | 8 x u8] = 24 bytes, unit 8 bytes (8-byte
     static constexpr int CHUNK_BYTES = 24;
     static constexpr int UNIT_BYTES = 8;
     struct Chunk { uint2 c0, c1, v; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t, uint32_t) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         const uint2* p2 = reinterpret_cast<const uint2*>(p);
         k.c0 = __ldg(p2);
         k.c1 = __ldg(p2 + 1);
@@ -596,7 +581,7 @@ struct Rec32V {
     static constexpr int UNIT_BYTES = CHUNK_BYTES % 32 == 0 ? 32 : (CHUNK_BYTES % 16 == 0 ? 16 : 8);
     static constexpr int WORDS = CHUNK_BYTES / 4;
     struct Chunk { uint32_t w[WORDS]; };
-    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t, uint32_t) {
+    static __device__ __forceinline__ void load(const char* p, Chunk& k, uint32_t) {
         if constexpr (CHUNK_BYTES % 16 == 0) {
             const uint4* p4 = reinterpret_cast<const uint4*>(p);
 #pragma unroll
@@ -638,7 +623,7 @@ __device__ __forceinline__ float score_rec(const char* __restrict__ rec, uint32_
     float acc = 0.f;
     for (uint32_t m = lane8; m < nch; m += 8) {
         typename R::Chunk k;
-        R::load(rec + (size_t)R::CHUNK_BYTES * m, k, m, nch);
+        R::load(rec + (size_t)R::CHUNK_BYTES * m, k, m);
         acc = R::dot(acc, k, q, scale);
     }
     return acc;
@@ -670,14 +655,14 @@ __device__ __forceinline__ void score_docs(const uint4* __restrict__ fwd, const 
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 c[j] = make_uint4(0, 0, 0, 0), v[j] = make_uint4(0, 0, 0, 0);
-                if (m < nch[j]) ld_chunk(rec[j] + (size_t)256 * r, m, nch[j], c[j], v[j]);
+                if (m < nch[j]) ld_chunk(reinterpret_cast<const uint4*>(rec[j] + (size_t)256 * r), (lane8 >> 2) & 1u, c[j], v[j]);
             }
             q.dot2x(acc[0], acc[1], c, v);
         } else {
             typename R::Chunk k[D];
 #pragma unroll
             for (int j = 0; j < D; ++j)
-                if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j], m, nch[j]);
+                if (m < nch[j]) R::load(rec[j] + (size_t)R::CHUNK_BYTES * 8 * r, k[j], m);
 #pragma unroll
             for (int j = 0; j < D; ++j)
                 if (m < nch[j]) acc[j] = R::dot(acc[j], k[j], q, scale);
@@ -1196,7 +1181,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
         const uint32_t w_wkey = s_wkey;
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_tma_bar[TMA ? warp : 0]);
         const uint32_t stage = tma_ring_s + warp * TMA_WARP_BYTES + (lane >> 3) * 2 * TMA_ROUND_BYTES;  // this group's two rounds
-        [[maybe_unused]] const uint32_t sw = (lane8 >> 2) & 1u;
+        const uint32_t sw = (lane8 >> 2) & 1u;
         auto load_posts = [&](uint32_t dbase, uint64_t (&post)[2], uint32_t (&slot)[2]) -> uint32_t {
             uint32_t mx = 0;
 #pragma unroll
@@ -1252,16 +1237,9 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 tma_par ^= 1u;
                 uint4 c[2], v[2];
                 c[0] = c[1] = v[0] = v[1] = make_uint4(0, 0, 0, 0);
-#if SGPU_REC16_PLANAR  // staged round = [components of its T chunks | their values]: 8 lanes read 128 contiguous bytes
-                const uint32_t at = stage + 16 * lane8;
-                if (m < nch0) c[0] = lds128(at), v[0] = lds128(at + 16 * min(8u, nch0 - 8 * r));
-                if (m < nch1)
-                    c[1] = lds128(at + TMA_ROUND_BYTES), v[1] = lds128(at + TMA_ROUND_BYTES + 16 * min(8u, nch1 - 8 * r));
-#else
                 const uint32_t at = stage + 32 * lane8 + 16 * sw;
                 if (m < nch0) c[0] = lds128(at), v[0] = lds128(at ^ 16u);
                 if (m < nch1) c[1] = lds128(at + TMA_ROUND_BYTES), v[1] = lds128((at + TMA_ROUND_BYTES) ^ 16u);
-#endif
                 __syncwarp();  // every lane holds its chunks in registers: the stage is free
                 if (r + 1 < rounds) issue(post, r + 1);
                 else if (dbase + 2 * GROUPS < n) issue(post_n, 0);

@@ -4,10 +4,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#ifndef SGPU_REC16_PLANAR
-#define SGPU_REC16_PLANAR 1  // u16 / f16 records stored round-planar (search.cuh, ld_chunk; kernels.cuh, k_pack_records)
-#endif
-
 namespace sgpu {
 
 struct ListHdr {
