@@ -287,7 +287,7 @@ __global__ void k_pack_records(const uint64_t* fwd_off, const uint16_t* comps, c
     for (uint32_t i = lane; i < nch * 8; i += 32) {
         const uint32_t ch = i >> 3, j = i & 7;
         const bool ok = i < len;
-        const uint32_t sw = (ch & 4u) ? 8u : 0u;  // chunks 4..7 of a round: [values | components] (search.cuh, ld_chunk)
+        const uint32_t sw = (!SGPU_LD256 && (ch & 4u)) ? 8u : 0u;  // chunks 4..7 of a round: [values | components] (search.cuh, ld_chunk)
         rec[ch * 16 + sw + j] = ok ? comps[e0 - elem0 + i] : (uint16_t)0;
         rec[ch * 16 + (8 - sw) + j] = ok ? vals[e0 - elem0 + i] : (uint16_t)0;
     }

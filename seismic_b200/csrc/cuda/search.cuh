@@ -91,13 +91,21 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
                  : "l"(p));
     return r;
 }
-// One 32-byte chunk of the u16 / f16 layout (8 components + 8 values) with two 128-bit loads.  Chunks 4..7 of every
-// round of 8 are stored [values | components] instead of [components | values] (`sw` = bit 2 of the chunk index): when
-// the 8 lanes of a group read the same half of their chunks from SHARED memory (TMA-staged rounds) the 16-byte pieces
-// then fall into 8 distinct bank quads; from global memory the order is irrelevant.
+// One 32-byte chunk of the u16 / f16 layout (8 components + 8 values) with ONE 256-bit load (ld.global.nc.v8, sm_100):
+// 4.59 vs 4.89 ms per 10 k queries against two 128-bit loads of the same sector (profiles/r2_variants_ld256.log) — half
+// the load instructions and no second lookup of every sector in L1.
+// (SGPU_LD256 = 0, the previous layout: chunks 4..7 of every round of 8 stored [values | components] — `sw` = bit 2 of
+// the chunk index — so that the 8 lanes of a group reading the same half of their chunks from SHARED memory in the
+// TMA-staged variant fall into 8 distinct bank quads.)
 __device__ __forceinline__ void ld_chunk(const uint4* p, uint32_t sw, uint4& c, uint4& v) {
+#if SGPU_LD256
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+#else
     c = ld_stream(p + sw);
     v = ld_stream(p + (sw ^ 1u));
+#endif
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -1237,7 +1245,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                 tma_par ^= 1u;
                 uint4 c[2], v[2];
                 c[0] = c[1] = v[0] = v[1] = make_uint4(0, 0, 0, 0);
-                const uint32_t at = stage + 32 * lane8 + 16 * sw;
+                const uint32_t at = stage + 32 * lane8 + (SGPU_LD256 ? 0u : 16 * sw);
                 if (m < nch0) c[0] = lds128(at), v[0] = lds128(at ^ 16u);
                 if (m < nch1) c[1] = lds128(at + TMA_ROUND_BYTES), v[1] = lds128((at + TMA_ROUND_BYTES) ^ 16u);
                 __syncwarp();  // every lane holds its chunks in registers: the stage is free

@@ -4,6 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef SGPU_LD256
+#define SGPU_LD256 1  // u16 x 16-bit-value records: one 256-bit load per 32-byte chunk (0: two 128-bit loads, swapped layout)
+#endif
+
 namespace sgpu {
 
 struct ListHdr {

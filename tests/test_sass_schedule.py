@@ -2,8 +2,9 @@
 
 The scoring loop runs at the 64-register limit of 4 CTAs x 256 threads per SM.  One register too many and ptxas sinks
 the second document's gathers below the first document's table lookups, which halves the bytes in flight per warp
-(measured on B200: 5.3 -> 6.2 ms per 10 k queries).  This test pins the good schedule: the four 128-bit gathers of an
-iteration are issued before the first query-table lookup, and the kernel neither spills nor exceeds 64 registers."""
+(measured on B200: 5.3 -> 6.2 ms per 10 k queries).  This test pins the good schedule: the two 256-bit gathers of an
+iteration (one per document of the group; four 128-bit ones in builds with SGPU_LD256 = 0) are issued before the first
+query-table lookup, and the kernel neither spills nor exceeds 64 registers."""
 import re
 import shutil
 import subprocess
@@ -30,15 +31,15 @@ def test_hot_loop_issues_all_gathers_before_the_first_lookup():
     assert start >= 0, "benchmark instantiation of k_search not found in the library"
     end = sass.find("Function : ", start + 10)
     ops = [m.group(1) for m in re.finditer(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", sass[start:end], re.M)]
-    is_gather = lambda o: re.match(r"LDG\.E(\.NA)?\.128\.CONSTANT", o) is not None  # noqa: E731  (ld.global.nc[.L1::no_allocate].v4)
+    is_gather = lambda o: re.match(r"LDG\.E(\.NA|\.ENL2)?\.(128|256)\.CONSTANT", o) is not None  # noqa: E731  (ld.global.nc .v4 / .v8)
     first = next(i for i, o in enumerate(ops) if is_gather(o))
-    gathers = 0
+    bits = 0
     for o in ops[first:]:
         if is_gather(o):
-            gathers += 1
+            bits += 256 if ".256." in o else 128
         elif o.startswith("LDS.U8"):
             break
-    assert gathers == 4, "ptxas no longer issues the 4 gathers of a scoring iteration back to back (%d)" % gathers
+    assert bits == 512, "ptxas no longer issues the gathers of a scoring iteration (2 x 32 bytes) back to back (%d bits)" % bits
 
 
 def test_benchmark_kernel_fits_four_ctas_per_sm_without_spills():
