@@ -1572,26 +1572,30 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     // (Pushing a whole group speculatively and rolling back when a later block no longer passes
                     // against the final theta was measured: the rollbacks of the first, estimate-sorted list cost more
                     // than the merged pushes save — 5.33 vs 5.18 ms at k = 10, 26.4 vs 19.2 ms at k = 100.)
-                    uint32_t j0 = 0;
-                    while (j0 < n_cand) {
+                    // (lane <-> candidate is fixed per group of 32, so a block's bounds, estimate and best survivor are
+                    // read once; theta only grows, so after a push the remaining lanes are simply re-tested.)
+                    for (uint32_t j0 = 0; j0 < n_cand; j0 += 32) {
                         const uint32_t j = j0 + lane;
                         const bool valid = j < n_cand;
                         const uint32_t s0 = valid && j ? cand_end[j - 1] : 0u, s1 = valid ? cand_end[j] : 0u;
                         const uint32_t mx = valid ? cand_mx[j] : 0u;
-                        const bool has = mx != 0u && (!heap.full() || mx >= total_key(heap.theta));
-                        const bool passes =
-                            valid && !(heap.full() && cand_est[j] < __fmul_rn(a.heap_factor, heap.theta));
-                        const uint32_t pm = __ballot_sync(0xffffffffu, passes);
-                        const uint32_t hm = __ballot_sync(0xffffffffu, passes && has);
-                        if (!hm) {
-                            st_pushed += __popc(pm);
-                            j0 += 32;
-                            continue;
+                        const float ce = valid ? cand_est[j] : 0.f;
+                        uint32_t live = __ballot_sync(0xffffffffu, valid);  // blocks of the group not yet decided
+                        while (live) {
+                            const bool has = mx != 0u && (!heap.full() || mx >= total_key(heap.theta));
+                            const bool passes = valid && !(heap.full() && ce < __fmul_rn(a.heap_factor, heap.theta));
+                            const uint32_t pm = __ballot_sync(0xffffffffu, passes) & live;
+                            const uint32_t hm = __ballot_sync(0xffffffffu, passes && has) & live;
+                            if (!hm) {
+                                st_pushed += __popc(pm);
+                                break;
+                            }
+                            const int f = __ffs(hm) - 1;
+                            const uint32_t upto = (2u << f) - 1u;  // lanes 0 .. f (f = 31: all)
+                            st_pushed += __popc(pm & upto);
+                            push_range(__shfl_sync(0xffffffffu, s0, f), __shfl_sync(0xffffffffu, s1, f));
+                            live &= ~upto;
                         }
-                        const int f = __ffs(hm) - 1;
-                        st_pushed += __popc(pm & ((2u << f) - 1u));
-                        push_range(__shfl_sync(0xffffffffu, s0, f), __shfl_sync(0xffffffffu, s1, f));
-                        j0 += (uint32_t)f + 1;
                     }
                     if (lane == 0) s_full = heap.full(), s_theta = heap.theta, s_wkey = heap.wkey;
                 }
