@@ -136,3 +136,36 @@ def test_oracle_matches_python_restatement_random_configs(oracle_mod, seed):
         p_ids, p_sc, ev = py.search(c, v, k, cut, hf, n_knn=n_knn, first_sorted=srt)
         assert cnt[0] == len(p_ids) and ids[0, : cnt[0]].tolist() == p_ids
         assert np.array_equal(sc[0, : cnt[0]], np.array(p_sc, np.float32)) and st["blocks_evaluated"] == ev
+
+
+def test_dotvbyte_long_records_and_mixed_chunks():
+    """DotVByte records with more than 64 chunks (several directory entries, `wide chunks before` > 0), narrow and wide
+    chunks mixed, first components above and below 256, an empty document: builder, independent Python decoder and the
+    library's host decoder agree on every component and code."""
+    from seismic_b200 import Dataset, HostIndex
+    rng = np.random.default_rng(11)
+    comps, vals = [], []
+    for i in range(120):
+        n = int(rng.integers(1, 1400))
+        if i % 3 == 0:    # dense low range: almost every gap fits one byte (narrow chunks)
+            c = np.sort(rng.choice(4000, size=min(n, 3000), replace=False))
+        elif i % 3 == 1:  # sparse: almost every gap needs two bytes
+            c = np.sort(rng.choice(65000, size=min(n, 200), replace=False))
+        else:             # clusters: runs of small gaps separated by large ones
+            base = np.sort(rng.choice(60000, size=12, replace=False))
+            c = np.unique(np.concatenate([b + rng.choice(300, size=min(n // 12 + 1, 250), replace=False) for b in base]))
+        comps.append(c.astype(np.uint32))
+        vals.append((rng.random(len(c), dtype=np.float32) * 3 + 0.01).astype(np.float32))
+    comps.append(np.empty(0, np.uint32)); vals.append(np.empty(0, np.float32))
+    index = HostIndex.build(Dataset.from_lists(comps, vals, dim=65536), n_postings=20)
+    vb = index.convert_to_dotvbyte()
+    off, dc, dv, codes = decode_dotvbyte(vb)   # asserts the directory, the wide flags and the padding on the way
+    o0, c0, v0 = index.forward_csr()
+    assert np.array_equal(off, o0) and np.array_equal(dc, c0)
+    assert int(np.diff(o0.astype(np.int64)).max()) > 64 * 8, "no record with more than one directory entry"
+    assert np.all(np.abs(dv - v0) <= float(vb.view.value_scale) / 2 + 1e-6)
+    for d in (0, 1, 2, 57, len(comps) - 1):
+        gc, gv = vb.get_doc(d)
+        assert np.array_equal(gc, dc[int(off[d]):int(off[d + 1])]) and np.array_equal(gv, dv[int(off[d]):int(off[d + 1])])
+    f16, packed = index.space_usage()["forward"], vb.space_usage()["forward"]
+    assert packed < 0.85 * f16
