@@ -1473,38 +1473,24 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                         }
                 }
                 if (lane == 31) s_warp_docs[warp] = cd, s_warp_cnt[warp] = cc;
-                if (tid == 0) s_first_rej = 0xffffffffu;
+                if (tid == 0) s_first_rej = 0xffffffffu, s_wave_docs = 0, s_wave_cnt = 0, s_big_nd = 0;  // the previous
+                                                                                   // wave's totals are consumed
                 __syncthreads();
-                if (tid == 0) s_wave_docs = 0, s_wave_cnt = 0, s_big_nd = 0;  // previous wave's totals are consumed
-                if (warp == 0) {
-                    uint32_t wd = lane < NW ? s_warp_docs[lane] : 0u, wc = lane < NW ? s_warp_cnt[lane] : 0u;
-#pragma unroll
-                    for (int sft = 1; sft < NW; sft <<= 1) {
-                        const uint32_t od = __shfl_up_sync(0xffffffffu, wd, sft);
-                        const uint32_t oc = __shfl_up_sync(0xffffffffu, wc, sft);
-                        if (lane >= (uint32_t)sft) wd += od, wc += oc;
-                    }
-                    if (lane < NW) s_warp_docs[lane] = wd, s_warp_cnt[lane] = wc;
-                }
-                __syncthreads();
-                // exclusive prefix of this thread (documents / passing blocks before its first position)
+                // exclusive prefix of this thread (documents / passing blocks before its first position): every warp adds
+                // up the totals of the warps before it itself — one barrier less than a scan by warp 0
                 uint32_t bd = cd - cd_t, bc = cc - cc_t;
-                if (warp > 0) bd += s_warp_docs[warp - 1], bc += s_warp_cnt[warp - 1];
+                for (uint32_t w = 0; w < warp; ++w) bd += s_warp_docs[w], bc += s_warp_cnt[w];
                 // accept while the wave stays within its soft cap; the first passing block is accepted whenever it
-                // fits the buffer; a first passing block larger than the buffer is processed alone, in parts
+                // fits the buffer; a first passing block larger than the buffer is processed alone, in parts.  The running
+                // sums only grow, so the accepted blocks are a prefix of the passing ones: a passing block is in the wave
+                // iff it is accepted, and the first rejected position is only needed to restart the next pass.
 #pragma unroll
                 for (int i = 0; i < SP; ++i) {
                     const uint32_t cdi = bd + cdl[i], cci = bc + ccl[i];
                     const bool accepted = pass[i] && cdi <= (cci == 1 ? a.buf_docs : cap) && cci <= a.cand_cap;
                     if (pass[i] && !accepted) atomicMin(&s_first_rej, pos0 + SP * tid + i);
                     if (pass[i] && cci == 1 && !accepted) s_big_nd = nd[i], s_big_p0 = p0[i];
-                }
-                __syncthreads();
-                const uint32_t first_rej = s_first_rej;
-#pragma unroll
-                for (int i = 0; i < SP; ++i) {
-                    const uint32_t cdi = bd + cdl[i], cci = bc + ccl[i];
-                    if (pass[i] && pos0 + SP * tid + i < first_rej) {
+                    if (accepted) {
                         cand_end[cci - 1] = cdi;
                         cand_est[cci - 1] = e[i];
                         cand_p0[cci - 1] = p0[i];
@@ -1514,6 +1500,7 @@ __global__ void __launch_bounds__(T, OCC) k_search(const SearchArgs a) {
                     }
                 }
                 __syncthreads();
+                const uint32_t first_rej = s_first_rej;
                 const uint32_t n_docs = s_wave_docs, n_cand = s_wave_cnt, big_nd = s_big_nd, big_p0 = s_big_p0;
                 lap(1);
                 if (n_cand == 0 && big_nd) {
