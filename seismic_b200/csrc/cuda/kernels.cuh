@@ -13,7 +13,7 @@
 //   fwd records       one record per document, 32-byte aligned, made of 32-byte chunks
 //                     [8 x u16 component | 8 x f16 value]; the tail chunk is padded with
 //                     (component 0, value +0.0).  A group of 8 lanes reads 8 consecutive chunks
-//                     = 256 contiguous bytes with two 128-bit loads per lane; every fetched
+//                     = 256 contiguous bytes with one 256-bit load per lane; every fetched
 //                     32-byte sector is fully used.
 //   rec_start[N+1]    u32 record start (32-byte units) per doc, for key -> doc id mapping
 //
