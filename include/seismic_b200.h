@@ -179,8 +179,14 @@ int sgpu_index_set_stream(SgpuIndex* index, void* cuda_stream);
  * on the device side.  Not available for DotVByte indexes (the reference class has no kNN, src/pylib/dotvbyte.rs). */
 int sgpu_index_set_knn(SgpuIndex* index, const uint64_t* neighbours, uint32_t knn_dim);
 
-/* Tuning knobs (do not change results): wave sizes of the speculative block scheduler, CTA count.
- * name in {"wave_docs","first_wave_docs","ctas","scratch_mb"}; returns SGPU_EINVAL for unknown. */
+/* Tuning knobs (they never change results; tests/test_gpu_parity.py runs every one of them against the oracle):
+ *   scheduler     "hq_wave_docs", "hq_first_wave_docs", "hq_cand_cap" (compact-query kernel), "wave_docs",
+ *                 "first_wave_docs", "ctas" (long-query kernel), "hq_ctas_per_sm", "hq_carveout_pct", "bucket",
+ *                 "scratch_mb" (per-batch scratch; larger batches run in chunks)
+ *   kernel build  "hq" (query table: 0 long-query kernel only, 1 byte index, 2 perfect hash, 3 bitmap + rank), "tma" (records staged by bulk
+ *                 copies), "occ16" / "occvb" / "occ32" (documents in flight per 8-lane group and CTAs per SM of the
+ *                 u16 / DotVByte / u32 kernels), "wide_heap" (register heap for 32 < k <= 128), "order_warp"
+ * Returns SGPU_EINVAL for unknown names. */
 int sgpu_index_set_option(SgpuIndex* index, const char* name, int64_t value);
 
 /* Exact top-k by brute force over the forward index (ground truth for recall; mirrors
