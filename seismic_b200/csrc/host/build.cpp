@@ -682,7 +682,8 @@ int build_index(const ShostDataset& ds, const ShostBuildConfig& cfg_in, ShostInd
                 cp(sc_run_off + lss[c] + c, o.sc_run_off);
                 cp(ent_blk + les[c], o.ent_blk);
                 cp(ent_code + les[c], o.ent_code);
-                ListOut().postings.swap(o.postings);
+                o = ListOut();  // release the list's buffers as soon as they are copied: the sections are first-touched
+                                // while the per-list copies go away, instead of both being resident at the end
             }
         });
     }
